@@ -1,0 +1,204 @@
+/*
+ * selfocc_b200 -- C ABI of the sm_100a hot-path library (libselfocc_b200.so).
+ *
+ * The reference (huang-yh/SelfOcc) has no FFI of its own: its boundary for this path is the
+ * mmengine registry + nn.Module contracts.  This C ABI sits UNDER
+ * those Python modules; each entry point names the reference call site it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are dense, row-major, fp32 unless stated; index tensors are int64/int32 as stated;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - no internal allocation, no implicit synchronisation: work is enqueued on `stream`;
+ *   - return value: SO_OK (0) or a negative SO_ERR_* code; never throws, never prints;
+ *   - thread-safe for concurrent callers that use distinct streams and distinct outputs.
+ */
+#ifndef SELFOCC_B200_H
+#define SELFOCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO_OK 0
+#define SO_ERR_INVALID_ARG (-1)   /* null pointer / non-positive size / unsupported shape */
+#define SO_ERR_UNSUPPORTED (-2)   /* valid request outside what the kernels implement */
+#define SO_ERR_CUDA (-3)          /* a CUDA runtime call or launch failed; see so_last_cuda_error */
+#define SO_ERR_NO_DEVICE (-4)
+
+#define SO_ABI_VERSION 1
+
+/* ABI version of the loaded library (compare with SO_ABI_VERSION). */
+int so_abi_version(void);
+/* cudaError_t (as int) of the most recent failing CUDA call on this host thread, 0 if none. */
+int so_last_cuda_error(void);
+/* Static string for an SO_* code. */
+const char* so_error_string(int code);
+/* Number of kernel launches enqueued by this library since process start (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t so_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Grid <-> metre mapping, one axis.  Restates LinearMapping.meter2grid
+ * (reference model/encoder/bevformer/mappings.py:97-150):
+ *     c = m - start;  a = |c|
+ *     g = sign(c) * (a <= range0 || size1 == 0 ? a / range0 * size0
+ *                                             : size0 + (a - range0) / range1 * size1) + offset
+ * offset = size0 + size1 for a mirrored (non-half) h/w axis, else 0; start = d_range[0] for d.
+ * Axis order everywhere: [0] = h (from metre y), [1] = w (from metre x), [2] = d (from metre z).
+ */
+typedef struct so_axis_map {
+  float start, range0, range1, size0, size1, offset;
+} so_axis_map;
+
+typedef struct so_volume_desc {
+  int32_t H, W, Z;      /* grid sizes (size_h, size_w, size_d) */
+  int32_t zpitch;       /* floats between consecutive (h, w) columns of the sdf plane, >= Z */
+  int32_t n_feat;       /* decoded channels besides sdf (colour + semantics), 0 if none */
+  int32_t feat_pitch;   /* floats per voxel in the channel-last feature volume (>= n_feat, %4==0) */
+  so_axis_map axis[3];
+} so_volume_desc;
+
+/* ---------------------------------------------------------------------------------------
+ * B5  TPV planes -> decoded volume.  Replaces field.pre_compute_density_color(representation)
+ * (call sites model/head/neus_head/neus_head.py:249,302,483; semantics from the in-repo analogue
+ * model/head/nerfacc_head/bev_nerf.py:62-95, tpv=True, density_layers=2):
+ *     f[h,w,z,:] = hw[h,w,:] + zh[z,h,:] + wz[w,z,:]
+ *     out        = W2 * softplus(W1 * softplus(f) + b1) + b2          (C -> C -> 1 + n_feat)
+ * tpv_hw [H*W, C], tpv_zh [Z*H, C], tpv_wz [W*Z, C]; w1 [C, C], b1 [C], w2 [1+n_feat, C], b2.
+ * Outputs: vol_sdf [H, W, zpitch] (channel 0; pad entries zeroed), vol_feat [H, W, Z, feat_pitch]
+ * (channels 1.., may be NULL when n_feat == 0).  C must be a multiple of 32, C <= 128.
+ */
+int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C,
+                  const float* w1, const float* b1, const float* w2, const float* b2,
+                  const so_volume_desc* vol_host, float* vol_sdf, float* vol_feat, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Ray set of one frame: n_cam cameras x rays_per_cam pixel rays, flattened (cam, ray)-major
+ * exactly like neus_head.py:324-325.  Pixel coordinates come either from `pix` ([rays_per_cam, 2]
+ * (x, y), RaySampler.forward(), ray_sampler.py:48-68) or, when pix == NULL, from the strided grid
+ *     x = j * sx + ox,  y = i * sy + oy,  ray = i * nx + j          (ray_sampler.py:23-31,58-68)
+ * cam_mats [n_cam, 4, 4] = metas[trans_kw] (img2lidar.py:25-70): origin = M[:3,3],
+ * direction = M[:3,:3] * (x, y, 1), un-normalised; its norm converts ray length <-> camera depth.
+ */
+typedef struct so_ray_desc {
+  int32_t n_cam, rays_per_cam;
+  int32_t nx, ny;            /* grid shape, used when pix == NULL (nx * ny == rays_per_cam) */
+  float sx, ox, sy, oy;
+  int64_t ray_begin;         /* first flat ray index this call renders (ray sharding across GPUs) */
+  int64_t ray_count;         /* number of flat rays this call renders */
+  int64_t chunk_len;         /* rays per reference chunk (neus_head.py:341-345 `--batch`); the
+                                expected-depth clip is taken per chunk.  <= 0: one chunk */
+} so_ray_desc;
+
+typedef struct so_render_params {
+  float aabb[6];             /* roi_aabb x0 y0 z0 x1 y1 z1 (neus_head.py:189-195) */
+  float near_plane;          /* near clamp, applied when `training` (collider) */
+  int32_t training;          /* 0: eval (near clamp 0, rgb clamped), 1: train */
+  int32_t num_samples;       /* S, uniform bins per ray (neus_head.py:136) */
+  float inv_s;               /* exp(10 * variance) of the deviation network, clipped 1e-6..1e6 */
+  float cos_anneal;          /* NeuS cos anneal ratio, 1.0 after warm-up */
+  int32_t anchor_mid;        /* 1: field queried at bin midpoints, 0: at bin starts */
+  int32_t sh_act;            /* 0: relu(C0*f + 0.5), 1: sigmoid(C0*f)  (sh_render.py:84-94, deg 0) */
+  int32_t bkgd_mode;         /* 0 black, 1 white, 2 per-ray colours given in bkgd_rand */
+} so_render_params;
+
+/* Workspace floats needed by so_render_infer for `n_chunks` depth-clip chunks. */
+int64_t so_render_workspace_floats(int64_t n_chunks);
+
+/* B1-B4, B6-B11  fused inference render: ray generation -> AABB -> S samples -> trilinear gather
+ * (+ analytic sdf gradient) -> NeuS alpha -> compositing -> depth / max-depth / acc / normal / rgb.
+ * Replaces the chunk loop `self.model(ray_bundle)` + post-processing of NeuSHead.render
+ * (model/head/neus_head/neus_head.py:319-438).  Outputs are indexed by (flat ray - ray_begin);
+ * any output pointer may be NULL.  depth/max_depth are camera-z depths (divided by |direction|).
+ *   depth [n], max_depth [n], max_idx int64 [n] (first-max argmax of w/delta, :430-438),
+ *   acc [n], normal_vis [n,3], rgb [n,3] (needs n_feat >= 3), sem [n, n_feat-3] (needs n_feat > 3).
+ * workspace: so_render_workspace_floats(n_chunks) floats, n_chunks = ceil(total rays / chunk_len).
+ */
+int so_render_infer(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                    const float* cam_mats, const float* pix, const so_ray_desc* rays_host,
+                    const so_render_params* params_host, const float* bkgd_rand,
+                    float* depth, float* max_depth, int64_t* max_idx, float* acc,
+                    float* normal_vis, float* rgb, float* sem, float* workspace, void* stream);
+
+/* B12  field query at arbitrary points.  Replaces field.forward_sdfnetwork / forward_geonetwork
+ * as used by NeuSHead.get_uniform_sdf (neus_head.py:265-293).  points [n,3] metres ->
+ * sdf [n], grad [n,3] (NULL ok), feat [n, n_feat] raw decoded channels 1.. (NULL ok). */
+int so_field_query(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                   const float* points, int64_t n, float* sdf, float* grad, float* feat, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A7/A8  multi-scale deformable attention forward.  Drop-in for
+ * MultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index,
+ * sampling_locations, attention_weights, im2col_step) of mmcv==2.0.1 (reference call sites
+ * model/encoder/bevformer/attention/image_cross_attention.py:340-342 and
+ * model/encoder/tpvformer/attention/cross_view_hybrid_attention.py:111-113).
+ *   value [B, Nv, Hd, Dh]   spatial_shapes int64 [L,2] (h,w)   level_start_index int64 [L]
+ *   loc [B, Nq, Hd, L, P, 2] normalised (x,y)   weights [B, Nq, Hd, L, P]   out [B, Nq, Hd*Dh]
+ * Dh must be 16 or 32.
+ */
+int so_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                    const float* loc, const float* weights, float* out,
+                    int32_t B, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Nq, int32_t L, int32_t P,
+                    void* stream);
+
+/* Backward of so_msda_forward (the mmcv op's autograd contract): grad_out [B,Nq,Hd*Dh] ->
+ * grad_value [B,Nv,Hd,Dh] (must be zero-filled by the caller; accumulated atomically),
+ * grad_loc [B,Nq,Hd,L,P,2], grad_weights [B,Nq,Hd,L,P]. */
+int so_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                     const float* loc, const float* weights, const float* grad_out,
+                     float* grad_value, float* grad_loc, float* grad_weights,
+                     int32_t B, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Nq, int32_t L, int32_t P,
+                     void* stream);
+
+/* A4  projection of pillar reference points into the cameras.  Replaces point_sampling
+ * (model/encoder/bevformer/utils.py:116-206, no post_rots / focal_ratios branch).
+ *   ref_3d [D, Q, 3] metres, lidar2img [N, 4, 4], img_h/img_w = metas[0]['img_shape']
+ *   -> uv [N, Q, D, 2] normalised (x, y), mask uint8 [N, Q, D] (1 = in frustum),
+ *      vis uint8 [N, Q] = any_d mask (the per-camera query visibility of
+ *      image_cross_attention.py:92; NULL ok).
+ * Arithmetic order is fixed (plain fp32 mul/add, no FMA contraction) so that `mask`, an index-
+ * generating quantity, is reproducible bit for bit. */
+int so_point_sampling(const float* ref_3d, const float* lidar2img, int32_t D, int32_t Q, int32_t N,
+                      float img_h, float img_w, float* uv, uint8_t* mask, uint8_t* vis, void* stream);
+
+/* A5+A6+A7  rebatch-free image cross-attention core for one TPV plane.  Replaces the
+ * nonzero()/rebatch/scatter-add/count machinery of BEVCrossAttention.forward together with the
+ * location arithmetic, softmax and op call of BEVDeformableAttention.forward
+ * (model/encoder/bevformer/attention/image_cross_attention.py:84-136, 313-345):
+ *   for every query q:  slots[q] = (1 / max(1, #visible cams)) *
+ *        sum_{cam visible(q)} MSDA(value[cam], uv[cam,q,:] + offsets[q] / (w_l, h_l), softmax(logits[q]))
+ * where visible(q, cam) = vis[cam, q] = any_d mask[cam, q, d] (from so_point_sampling).  offsets/logits depend on the query only, so they
+ * are computed once per query instead of once per (camera, padded slot).
+ *   value [N, Nv, Hd, Dh] (after value_proj), offsets [Q, Hd, L, D, 2], logits [Q, Hd, L, D],
+ *   uv [N, Q, D, 2], vis uint8 [N, Q], spatial_shapes int64 [L,2], level_start_index int64 [L]
+ *   -> slots [Q, Hd*Dh] (input of output_proj), count int32 [Q] (NULL ok). */
+int so_tpv_cross_attn_forward(const float* value, const int64_t* spatial_shapes,
+                              const int64_t* level_start_index, const float* offsets, const float* logits,
+                              const float* uv, const uint8_t* vis, float* slots, int32_t* count,
+                              int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t D,
+                              void* stream);
+
+/* A5  visible-query index lists, as the reference builds them with nonzero()
+ * (image_cross_attention.py:90-94), without a host sync: for each camera, ascending int64 query
+ * indices with any in-frustum point.  index_lists [N, Q] (first lens[cam] entries valid),
+ * lens int32 [N].  Single-CTA-per-camera ordered compaction. */
+int so_visible_index_lists(const uint8_t* mask, int32_t N, int32_t Q, int32_t D,
+                           int64_t* index_lists, int32_t* lens, void* stream);
+
+/* A8 fused  cross-view hybrid (self) attention core: softmax + location arithmetic + sampling.
+ * Replaces cross_view_hybrid_attention.py:83-116.
+ *   value [Nv, Hd, Dh] (after value_proj; levels = the three planes), offsets [Q, Hd, L, P, 2],
+ *   logits [Q, Hd, L, P], ref [Q, L, P, 2] -> out [Q, Hd*Dh] (input of output_proj). */
+int so_tpv_self_attn_forward(const float* value, const int64_t* spatial_shapes,
+                             const int64_t* level_start_index, const float* offsets, const float* logits,
+                             const float* ref, float* out,
+                             int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFOCC_B200_H */

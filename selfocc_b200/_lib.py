@@ -1,0 +1,102 @@
+"""ctypes binding of libselfocc_b200.so (the C ABI in include/selfocc_b200.h).
+
+There is NO fallback: if the shared library is missing or an entry point is absent this module
+raises, and every op in ``selfocc_b200.ops`` raises when handed a non-CUDA tensor.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'lib', 'libselfocc_b200.so')
+ABI_VERSION = 1
+
+
+class AxisMap(C.Structure):
+    _fields_ = [('start', C.c_float), ('range0', C.c_float), ('range1', C.c_float), ('size0', C.c_float),
+                ('size1', C.c_float), ('offset', C.c_float)]
+
+
+class VolumeDesc(C.Structure):
+    _fields_ = [('H', C.c_int32), ('W', C.c_int32), ('Z', C.c_int32), ('zpitch', C.c_int32),
+                ('n_feat', C.c_int32), ('feat_pitch', C.c_int32), ('axis', AxisMap * 3)]
+
+
+class RayDesc(C.Structure):
+    _fields_ = [('n_cam', C.c_int32), ('rays_per_cam', C.c_int32), ('nx', C.c_int32), ('ny', C.c_int32),
+                ('sx', C.c_float), ('ox', C.c_float), ('sy', C.c_float), ('oy', C.c_float),
+                ('ray_begin', C.c_int64), ('ray_count', C.c_int64), ('chunk_len', C.c_int64)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [('aabb', C.c_float * 6), ('near_plane', C.c_float), ('training', C.c_int32),
+                ('num_samples', C.c_int32), ('inv_s', C.c_float), ('cos_anneal', C.c_float),
+                ('anchor_mid', C.c_int32), ('sh_act', C.c_int32), ('bkgd_mode', C.c_int32)]
+
+
+class TrainParams(C.Structure):
+    _fields_ = [('base', RenderParams), ('n_rays', C.c_int64)]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_L = C.c_int64
+_F = C.c_float
+
+# name -> (restype, argtypes); must list every symbol declared in include/selfocc_b200.h
+SIGNATURES = {
+    'so_abi_version': (C.c_int, []),
+    'so_last_cuda_error': (C.c_int, []),
+    'so_error_string': (C.c_char_p, [C.c_int]),
+    'so_launch_count': (C.c_int64, []),
+    'so_tpv_decode': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _P, _P, _P]),
+    'so_render_workspace_floats': (C.c_int64, [_L]),
+    'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'so_field_query': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _L, _P, _P, _P, _P]),
+    'so_msda_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'so_msda_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'so_point_sampling': (C.c_int, [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
+    'so_tpv_cross_attn_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'so_visible_index_lists': (C.c_int, [_P, _I, _I, _I, _P, _P, _P]),
+    'so_tpv_self_attn_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class SelfOccLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SelfOccLibraryError(
+            'libselfocc_b200.so not found at %s -- run `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU/PyTorch fallback for the hot path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise SelfOccLibraryError('symbol %s missing from %s' % (name, LIB_PATH)) from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.so_abi_version() != ABI_VERSION:
+        raise SelfOccLibraryError('ABI version mismatch: library %d, binding %d' % (lib.so_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        lib = load()
+        raise SelfOccLibraryError('%s failed: %s (code %d, cudaError %d)' % (
+            what, lib.so_error_string(code).decode(), code, lib.so_last_cuda_error()))
+
+
+def launch_count():
+    return int(load().so_launch_count())

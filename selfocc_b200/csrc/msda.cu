@@ -1,0 +1,456 @@
+// Image -> tri-plane lifting kernels.
+//
+// Thread mapping of every sampling kernel: one "item" = one (query, head); DH/4 lanes own an item and
+// each lane owns 4 consecutive channels (one float4) of the head, so a bilinear corner is one coalesced
+// 64-byte (DH=16) read per item and the (query, head*DH) output row is written as float4, 512 B per warp.
+// Value tensors are 30-65 MB fp32, i.e. L2-resident on B200 (126 MB): these kernels are L2/L1-gather
+// bound, not HBM bound.
+#include "common.cuh"
+#include <math.h>
+
+namespace so {
+
+constexpr int kMaxLevels = 8;
+
+struct Levels {
+  int n;
+  int h[kMaxLevels], w[kMaxLevels];
+  long long start[kMaxLevels];
+};
+
+__device__ __forceinline__ void load_levels(Levels& lv, const long long* __restrict__ shapes,
+                                            const long long* __restrict__ lsi, int L) {
+  // spatial_shapes / level_start_index are device int64 tensors (the mmcv op contract); every CTA
+  // copies the <= 8 entries into shared memory once.
+  if (threadIdx.x < L) {
+    lv.h[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    lv.w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    lv.start[threadIdx.x] = lsi[threadIdx.x];
+  }
+  if (threadIdx.x == 0) lv.n = L;
+  __syncthreads();
+}
+
+// bilinear read of 4 channels at normalised location (lx, ly) of level (Hl, Wl); align_corners=False,
+// zero padding (mmcv ms_deform_attn / F.grid_sample semantics).  vbase points at channel 0 of this lane
+// in pixel 0 of the level; pstride = floats between consecutive pixels.
+__device__ __forceinline__ float4 bilinear4(const float* __restrict__ vbase, int pstride, int Hl, int Wl, float lx, float ly) {
+  float x = lx * (float)Wl - 0.5f, y = ly * (float)Hl - 0.5f;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(y > -1.f && x > -1.f && y < (float)Hl && x < (float)Wl)) return r;
+  float xf = floorf(x), yf = floorf(y);
+  int x0 = (int)xf, y0 = (int)yf;
+  float fx = x - xf, fy = y - yf;
+  float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+  bool xa = x0 >= 0, xb = x0 + 1 < Wl, ya = y0 >= 0, yb = y0 + 1 < Hl;
+  const float* p = vbase + ((long long)y0 * Wl + x0) * pstride;
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v00 = (ya && xa) ? __ldg(reinterpret_cast<const float4*>(p)) : z;
+  float4 v01 = (ya && xb) ? __ldg(reinterpret_cast<const float4*>(p + pstride)) : z;
+  float4 v10 = (yb && xa) ? __ldg(reinterpret_cast<const float4*>(p + (long long)Wl * pstride)) : z;
+  float4 v11 = (yb && xb) ? __ldg(reinterpret_cast<const float4*>(p + (long long)(Wl + 1) * pstride)) : z;
+  r.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+  r.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+  r.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+  r.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+  return r;
+}
+
+// ---- A7/A8 generic op (the mmcv contract) -------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) msda_forward_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+                                                           const float* __restrict__ loc, const float* __restrict__ wts,
+                                                           float* __restrict__ out, int B, int Nv, int Hd, int Nq, int L, int P) {
+  constexpr int LPI = DH / 4;
+  __shared__ Levels lv;
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LPI;
+  int lc = (int)(t % LPI);
+  long long n_items = (long long)B * Nq * Hd;
+  if (item >= n_items) return;
+  int h = (int)(item % Hd);
+  long long bq = item / Hd;
+  int b = (int)(bq / Nq);
+  const int pstride = Hd * DH;
+  const float* lp = loc + item * (long long)L * P * 2;
+  const float* wp = wts + item * (long long)L * P;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const int Hl = lv.h[l], Wl = lv.w[l];
+    const float* vbase = value + (((long long)b * Nv + lv.start[l]) * Hd + h) * DH + lc * 4;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+      float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + l * P + p);
+      float aw = __ldg(wp + l * P + p);
+      float4 s = bilinear4(vbase, pstride, Hl, Wl, xy.x, xy.y);
+      acc.x = fmaf(aw, s.x, acc.x); acc.y = fmaf(aw, s.y, acc.y);
+      acc.z = fmaf(aw, s.z, acc.z); acc.w = fmaf(aw, s.w, acc.w);
+    }
+  }
+  *reinterpret_cast<float4*>(out + item * DH + lc * 4) = acc;
+}
+
+// Backward of the generic op.  Same mapping; channel reductions for grad_loc / grad_weights run over the
+// LPI lanes of an item with xor-shuffles; grad_value is accumulated with 128-bit vector atomics.
+template <int DH>
+__global__ void __launch_bounds__(256) msda_backward_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+                                                            const float* __restrict__ loc, const float* __restrict__ wts,
+                                                            const float* __restrict__ gout, float* __restrict__ gvalue,
+                                                            float* __restrict__ gloc, float* __restrict__ gw, int B, int Nv,
+                                                            int Hd, int Nq, int L, int P) {
+  constexpr int LPI = DH / 4;
+  __shared__ Levels lv;
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LPI;
+  int lc = (int)(t % LPI);
+  long long n_items = (long long)B * Nq * Hd;
+  bool live = item < n_items;
+  if (!live) item = n_items - 1;  // keep the warp converged for the shuffles
+  int h = (int)(item % Hd);
+  long long bq = item / Hd;
+  int b = (int)(bq / Nq);
+  const int pstride = Hd * DH;
+  const float* lp = loc + item * (long long)L * P * 2;
+  const float* wp = wts + item * (long long)L * P;
+  float4 go = __ldg(reinterpret_cast<const float4*>(gout + item * DH + lc * 4));
+  for (int l = 0; l < L; ++l) {
+    const int Hl = lv.h[l], Wl = lv.w[l];
+    const long long voff = (((long long)b * Nv + lv.start[l]) * Hd + h) * DH + lc * 4;
+    for (int p = 0; p < P; ++p) {
+      float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + l * P + p);
+      float aw = __ldg(wp + l * P + p);
+      float x = xy.x * (float)Wl - 0.5f, y = xy.y * (float)Hl - 0.5f;
+      float g_w = 0.f, g_x = 0.f, g_y = 0.f;
+      if (y > -1.f && x > -1.f && y < (float)Hl && x < (float)Wl) {
+        float xf = floorf(x), yf = floorf(y);
+        int x0 = (int)xf, y0 = (int)yf;
+        float fx = x - xf, fy = y - yf;
+        bool xa = x0 >= 0, xb = x0 + 1 < Wl, ya = y0 >= 0, yb = y0 + 1 < Hl;
+        long long o00 = voff + ((long long)y0 * Wl + x0) * pstride;
+        long long o01 = o00 + pstride, o10 = o00 + (long long)Wl * pstride, o11 = o10 + pstride;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v00 = (ya && xa) ? __ldg(reinterpret_cast<const float4*>(value + o00)) : z;
+        float4 v01 = (ya && xb) ? __ldg(reinterpret_cast<const float4*>(value + o01)) : z;
+        float4 v10 = (yb && xa) ? __ldg(reinterpret_cast<const float4*>(value + o10)) : z;
+        float4 v11 = (yb && xb) ? __ldg(reinterpret_cast<const float4*>(value + o11)) : z;
+        float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+        // dot products with grad_out over this lane's 4 channels
+        float d00 = go.x * v00.x + go.y * v00.y + go.z * v00.z + go.w * v00.w;
+        float d01 = go.x * v01.x + go.y * v01.y + go.z * v01.z + go.w * v01.w;
+        float d10 = go.x * v10.x + go.y * v10.y + go.z * v10.z + go.w * v10.w;
+        float d11 = go.x * v11.x + go.y * v11.y + go.z * v11.z + go.w * v11.w;
+        g_w = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+        g_x = aw * (float)Wl * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+        g_y = aw * (float)Hl * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+        if (live) {
+          float4 g;
+          if (ya && xa) { float s = aw * w00; g = make_float4(s * go.x, s * go.y, s * go.z, s * go.w); atomicAdd(reinterpret_cast<float4*>(gvalue + o00), g); }
+          if (ya && xb) { float s = aw * w01; g = make_float4(s * go.x, s * go.y, s * go.z, s * go.w); atomicAdd(reinterpret_cast<float4*>(gvalue + o01), g); }
+          if (yb && xa) { float s = aw * w10; g = make_float4(s * go.x, s * go.y, s * go.z, s * go.w); atomicAdd(reinterpret_cast<float4*>(gvalue + o10), g); }
+          if (yb && xb) { float s = aw * w11; g = make_float4(s * go.x, s * go.y, s * go.z, s * go.w); atomicAdd(reinterpret_cast<float4*>(gvalue + o11), g); }
+        }
+      }
+#pragma unroll
+      for (int s = LPI / 2; s > 0; s >>= 1) {
+        g_w += __shfl_xor_sync(0xffffffffu, g_w, s);
+        g_x += __shfl_xor_sync(0xffffffffu, g_x, s);
+        g_y += __shfl_xor_sync(0xffffffffu, g_y, s);
+      }
+      if (live && lc == 0) {
+        long long o = item * (long long)L * P + l * P + p;
+        gw[o] = g_w;
+        gloc[2 * o] = g_x;
+        gloc[2 * o + 1] = g_y;
+      }
+    }
+  }
+}
+
+// ---- softmax statistics of one item's logits, computed cooperatively by its LPI lanes -------------------
+template <int LPI>
+__device__ __forceinline__ void softmax_stats(const float* __restrict__ lg, int n, int lc, float& mx, float& inv_sum) {
+  float m = -INFINITY;
+  for (int i = lc; i < n; i += LPI) m = fmaxf(m, __ldg(lg + i));
+#pragma unroll
+  for (int s = LPI / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  float sum = 0.f;
+  for (int i = lc; i < n; i += LPI) sum += expf(__ldg(lg + i) - m);
+#pragma unroll
+  for (int s = LPI / 2; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  mx = m;
+  inv_sum = 1.0f / sum;
+}
+
+// ---- A5+A6+A7 fused, rebatch-free image cross-attention core --------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) tpv_cross_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
+                                                             const float* __restrict__ uv, const unsigned char* __restrict__ vis,
+                                                             float* __restrict__ slots, int* __restrict__ count, int N, int Nv,
+                                                             int Hd, int Q, int L, int D) {
+  constexpr int LPI = DH / 4;
+  __shared__ Levels lv;
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LPI;
+  int lc = (int)(t % LPI);
+  long long n_items = (long long)Q * Hd;
+  bool live = item < n_items;
+  if (!live) item = n_items - 1;
+  int h = (int)(item % Hd);
+  int q = (int)(item / Hd);
+  const int pstride = Hd * DH;
+  const int LD = L * D;
+  const float* op = offsets + item * (long long)LD * 2;
+  const float* lg = logits + item * (long long)LD;
+  float mx, inv_sum;
+  softmax_stats<LPI>(lg, LD, lc, mx, inv_sum);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int cam = 0; cam < N; ++cam) {
+    if (!__ldg(vis + (long long)cam * Q + q)) continue;  // image_cross_attention.py:92 (query visible in cam)
+    ++cnt;
+    const float* uvp = uv + ((long long)cam * Q + q) * D * 2;
+    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < L; ++l) {
+      const int Hl = lv.h[l], Wl = lv.w[l];
+      const float fw = (float)Wl, fh = (float)Hl;
+      const float* vbase = value + (((long long)cam * Nv + lv.start[l]) * Hd + h) * DH + lc * 4;
+#pragma unroll 4
+      for (int d = 0; d < D; ++d) {
+        float2 r = __ldg(reinterpret_cast<const float2*>(uvp) + d);
+        float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * D + d);
+        float aw = expf(__ldg(lg + l * D + d) - mx) * inv_sum;
+        // image_cross_attention.py:326-328: ref + offset / (w_l, h_l)
+        float4 s = bilinear4(vbase, pstride, Hl, Wl, r.x + o.x / fw, r.y + o.y / fh);
+        part.x = fmaf(aw, s.x, part.x); part.y = fmaf(aw, s.y, part.y);
+        part.z = fmaf(aw, s.z, part.z); part.w = fmaf(aw, s.w, part.w);
+      }
+    }
+    acc.x += part.x; acc.y += part.y; acc.z += part.z; acc.w += part.w;  // :129-131, camera order
+  }
+  if (!live) return;
+  float c = (float)max(cnt, 1);  // :133-136
+  acc.x /= c; acc.y /= c; acc.z /= c; acc.w /= c;
+  *reinterpret_cast<float4*>(slots + item * DH + lc * 4) = acc;
+  if (count && h == 0 && lc == 0) count[q] = cnt;
+}
+
+// ---- A8 fused cross-view hybrid attention core -----------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+                                                            const float* __restrict__ offsets, const float* __restrict__ logits,
+                                                            const float* __restrict__ ref, float* __restrict__ out, int Nv, int Hd,
+                                                            int Q, int L, int P) {
+  constexpr int LPI = DH / 4;
+  __shared__ Levels lv;
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LPI;
+  int lc = (int)(t % LPI);
+  long long n_items = (long long)Q * Hd;
+  bool live = item < n_items;
+  if (!live) item = n_items - 1;
+  int h = (int)(item % Hd);
+  int q = (int)(item / Hd);
+  const int pstride = Hd * DH;
+  const int LP = L * P;
+  const float* op = offsets + item * (long long)LP * 2;
+  const float* lg = logits + item * (long long)LP;
+  const float* rp = ref + (long long)q * LP * 2;
+  float mx, inv_sum;
+  softmax_stats<LPI>(lg, LP, lc, mx, inv_sum);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const int Hl = lv.h[l], Wl = lv.w[l];
+    const float fw = (float)Wl, fh = (float)Hl;
+    const float* vbase = value + ((long long)lv.start[l] * Hd + h) * DH + lc * 4;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+      float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l * P + p);
+      float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * P + p);
+      float aw = expf(__ldg(lg + l * P + p) - mx) * inv_sum;
+      float4 s = bilinear4(vbase, pstride, Hl, Wl, r.x + o.x / fw, r.y + o.y / fh);  // cross_view_hybrid_attention.py:97-99
+      acc.x = fmaf(aw, s.x, acc.x); acc.y = fmaf(aw, s.y, acc.y);
+      acc.z = fmaf(aw, s.z, acc.z); acc.w = fmaf(aw, s.w, acc.w);
+    }
+  }
+  if (live) *reinterpret_cast<float4*>(out + item * DH + lc * 4) = acc;
+}
+
+// ---- A4 point_sampling (bevformer/utils.py:116-206) ---------------------------------------------------------
+// One thread per (camera, query); it walks the query's pillar of D reference points.  The projection uses
+// plain fp32 mul/add in a fixed left-to-right order (no FMA contraction): `mask` generates index lists.
+__global__ void __launch_bounds__(256) point_sampling_kernel(const float* __restrict__ ref3d, const float* __restrict__ l2i,
+                                                             int D, int Q, int N, float img_h, float img_w,
+                                                             float* __restrict__ uv, unsigned char* __restrict__ mask,
+                                                             unsigned char* __restrict__ vis) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)N * Q) return;
+  int cam = (int)(t / Q), q = (int)(t % Q);
+  float m[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) m[i] = __ldg(l2i + cam * 16 + i);
+  const float eps = 1e-5f;
+  bool any = false;
+  for (int d = 0; d < D; ++d) {
+    const float* p = ref3d + ((long long)d * Q + q) * 3;
+    float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+    float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+    float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+    bool ok = cz > eps;
+    float den = fmaxf(cz, eps);
+    float u = __fdiv_rn(__fdiv_rn(cx, den), img_w);
+    float v = __fdiv_rn(__fdiv_rn(cy, den), img_h);
+    ok = ok && (v > 0.f) && (v < 1.f) && (u < 1.f) && (u > 0.f);
+    long long o = ((long long)cam * Q + q) * D + d;
+    uv[2 * o] = u;
+    uv[2 * o + 1] = v;
+    if (mask) mask[o] = ok ? 1 : 0;
+    any = any || ok;
+  }
+  if (vis) vis[(long long)cam * Q + q] = any ? 1 : 0;
+}
+
+// ---- A5 ordered index lists (nonzero) ---------------------------------------------------------------------
+// One CTA per camera; chunks of 1024 queries are compacted in order with a block-wide ballot scan.
+__global__ void __launch_bounds__(1024) visible_index_kernel(const unsigned char* __restrict__ mask, int Q, int D,
+                                                             long long* __restrict__ lists, int* __restrict__ lens) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base;
+  int cam = blockIdx.x;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < Q; q0 += 1024) {
+    int q = q0 + threadIdx.x;
+    bool v = false;
+    if (q < Q) {
+      const unsigned char* m = mask + ((long long)cam * Q + q) * D;
+      for (int d = 0; d < D; ++d) v = v || m[d];
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < wid; ++w) off += warp_cnt[w];
+    if (v) lists[(long long)cam * Q + off + __popc(bal & ((1u << lane) - 1u))] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lens[cam] = base;
+}
+
+}  // namespace so
+
+using namespace so;
+
+#define SO_DISPATCH_DH(Dh, EXPR16, EXPR32) \
+  do {                                     \
+    if ((Dh) == 16) { EXPR16; }            \
+    else if ((Dh) == 32) { EXPR32; }       \
+    else return SO_ERR_UNSUPPORTED;        \
+  } while (0)
+
+extern "C" int so_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                               const float* loc, const float* weights, float* out, int32_t B, int32_t Nv, int32_t Hd,
+                               int32_t Dh, int32_t Nq, int32_t L, int32_t P, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !loc || !weights || !out) return SO_ERR_INVALID_ARG;
+  if (B < 1 || Nv < 1 || Hd < 1 || Nq < 0 || L < 1 || P < 1) return SO_ERR_INVALID_ARG;
+  if (Nq == 0) return SO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
+  const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
+  long long threads = (long long)B * Nq * Hd * (Dh / 4);
+  unsigned grid = (unsigned)ceil_div64(threads, 256);
+  SO_DISPATCH_DH(Dh, (msda_forward_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, out, B, Nv, Hd, Nq, L, P)),
+                 (msda_forward_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, out, B, Nv, Hd, Nq, L, P)));
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                const float* loc, const float* weights, const float* grad_out, float* grad_value,
+                                float* grad_loc, float* grad_weights, int32_t B, int32_t Nv, int32_t Hd, int32_t Dh,
+                                int32_t Nq, int32_t L, int32_t P, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !loc || !weights || !grad_out || !grad_value || !grad_loc ||
+      !grad_weights)
+    return SO_ERR_INVALID_ARG;
+  if (B < 1 || Nv < 1 || Hd < 1 || Nq < 0 || L < 1 || P < 1) return SO_ERR_INVALID_ARG;
+  if (Nq == 0) return SO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
+  const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
+  long long threads = (long long)B * Nq * Hd * (Dh / 4);
+  unsigned grid = (unsigned)ceil_div64(threads, 256);
+  SO_DISPATCH_DH(Dh,
+                 (msda_backward_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, grad_out, grad_value, grad_loc, grad_weights, B, Nv, Hd, Nq, L, P)),
+                 (msda_backward_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, grad_out, grad_value, grad_loc, grad_weights, B, Nv, Hd, Nq, L, P)));
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_point_sampling(const float* ref_3d, const float* lidar2img, int32_t D, int32_t Q, int32_t N, float img_h,
+                                 float img_w, float* uv, uint8_t* mask, uint8_t* vis, void* stream) {
+  if (!ref_3d || !lidar2img || !uv) return SO_ERR_INVALID_ARG;
+  if (D < 1 || Q < 1 || N < 1 || !(img_h > 0.f) || !(img_w > 0.f)) return SO_ERR_INVALID_ARG;
+  long long n = (long long)N * Q;
+  point_sampling_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(ref_3d, lidar2img, D, Q, N, img_h, img_w,
+                                                                                         uv, mask, vis);
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                         const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
+                                         float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q,
+                                         int32_t L, int32_t D, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !uv || !vis || !slots) return SO_ERR_INVALID_ARG;
+  if (N < 1 || Nv < 1 || Hd < 1 || Q < 1 || L < 1 || D < 1) return SO_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
+  const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
+  long long threads = (long long)Q * Hd * (Dh / 4);
+  unsigned grid = (unsigned)ceil_div64(threads, 256);
+  SO_DISPATCH_DH(Dh,
+                 (tpv_cross_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)),
+                 (tpv_cross_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)));
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_tpv_self_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                        const float* offsets, const float* logits, const float* ref, float* out, int32_t Nv,
+                                        int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !ref || !out) return SO_ERR_INVALID_ARG;
+  if (Nv < 1 || Hd < 1 || Q < 1 || L < 1 || P < 1) return SO_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
+  const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
+  long long threads = (long long)Q * Hd * (Dh / 4);
+  unsigned grid = (unsigned)ceil_div64(threads, 256);
+  SO_DISPATCH_DH(Dh, (tpv_self_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)),
+                 (tpv_self_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)));
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_visible_index_lists(const uint8_t* mask, int32_t N, int32_t Q, int32_t D, int64_t* index_lists, int32_t* lens,
+                                      void* stream) {
+  if (!mask || !index_lists || !lens || N < 1 || Q < 1 || D < 1) return SO_ERR_INVALID_ARG;
+  visible_index_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(mask, Q, D, reinterpret_cast<long long*>(index_lists), lens);
+  note_launch(1);
+  return check_launch();
+}

@@ -1,0 +1,362 @@
+// SDF volume-render head kernels.
+//
+// so_render_infer: ONE fused launch per frame (plus a tiny depth-clip-bounds pre-pass) replacing the
+// reference's python chunk loop of `self.model(ray_bundle)` (neus_head.py:346-374) and its CPU
+// max-depth step (:430-438).  Mapping: one thread per ray, a warp = 32 horizontally adjacent pixels of
+// one camera, so the 8-corner gathers of a warp hit a handful of (h, w) columns of the L2-resident
+// decoded volume and the per-ray outputs are written fully coalesced.  The 256-sample compositing
+// recurrence is kept in registers in the reference's order (exclusive cumprod, first-max argmax).
+#include "common.cuh"
+#include <math.h>
+
+namespace so {
+
+struct RayDev {
+  const float* cam;  // [n_cam][16]
+  const float* pix;  // [rays_per_cam][2] or nullptr
+  int n_cam, rays_per_cam, nx;
+  float sx, ox, sy, oy;
+  long long ray_begin, ray_count, total, chunk_len;
+};
+
+struct RenderDev {
+  float lo[3], hi[3];
+  float near_clamp;
+  int S;
+  float inv_s, cos_anneal;
+  int anchor_mid, sh_act, bkgd_mode, eval_clamp;
+};
+
+__device__ __forceinline__ void make_ray(const RayDev& R, long long gid, float o[3], float d[3], float& nrm) {
+  int cam = (int)(gid / R.rays_per_cam);
+  int r = (int)(gid - (long long)cam * R.rays_per_cam);
+  float px, py;
+  if (R.pix) {
+    px = __ldg(R.pix + 2 * r);
+    py = __ldg(R.pix + 2 * r + 1);
+  } else {
+    int i = r / R.nx, j = r - i * R.nx;
+    px = __fadd_rn(__fmul_rn((float)j, R.sx), R.ox);  // ray_sampler.py:24-25,65-66 (mul then add)
+    py = __fadd_rn(__fmul_rn((float)i, R.sy), R.oy);
+  }
+  const float* M = R.cam + cam * 16;
+  float dx = __ldg(M + 0) * px + __ldg(M + 1) * py + __ldg(M + 2);
+  float dy = __ldg(M + 4) * px + __ldg(M + 5) * py + __ldg(M + 6);
+  float dz = __ldg(M + 8) * px + __ldg(M + 9) * py + __ldg(M + 10);
+  o[0] = __ldg(M + 3); o[1] = __ldg(M + 7); o[2] = __ldg(M + 11);
+  nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  d[0] = dx / nrm; d[1] = dy / nrm; d[2] = dz / nrm;
+}
+
+// upstream AABBBoxCollider: slab test with 1/(d + 1e-6)
+__device__ __forceinline__ void slab(const RenderDev& P, const float o[3], const float d[3], float& tn, float& tf) {
+  float nmax = -INFINITY, fmin = INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float inv = 1.0f / (d[a] + 1e-6f);
+    float t1 = (P.lo[a] - o[a]) * inv, t2 = (P.hi[a] - o[a]) * inv;
+    nmax = fmaxf(nmax, fminf(t1, t2));
+    fmin = fminf(fmin, fmaxf(t1, t2));
+  }
+  tn = fmaxf(nmax, P.near_clamp);
+  tf = fmaxf(fmin, tn + 1e-6f);
+}
+
+// torch.linspace(0, 1, S + 1)[i] in fp32 (two-sided evaluation like ATen's CPU kernel)
+__device__ __forceinline__ float bin_edge01(int i, int S, float step) {
+  return (i < (S + 1) / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(S - i)));
+}
+__device__ __forceinline__ float edge_t(float b, float tn, float tf) {
+  return __fadd_rn(__fmul_rn(b, tf), __fmul_rn(__fsub_rn(1.0f, b), tn));
+}
+
+// ---- pre-pass: per-chunk [min first-mid, max last-mid] for the expected-depth clip ------------------
+__global__ void bounds_init_kernel(float* ws, long long n_chunks) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n_chunks) {
+    ws[2 * i] = INFINITY;
+    ws[2 * i + 1] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) bounds_kernel(RayDev R, RenderDev P, float* ws) {
+  long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  bool ok = gid < R.total;
+  float mn = INFINITY, mx = 0.f;
+  long long chunk = 0;
+  if (ok) {
+    float o[3], d[3], nrm, tn, tf;
+    make_ray(R, gid, o, d, nrm);
+    slab(P, o, d, tn, tf);
+    float step = 1.0f / (float)P.S;
+    float e0 = edge_t(bin_edge01(0, P.S, step), tn, tf), e1 = edge_t(bin_edge01(1, P.S, step), tn, tf);
+    float eL = edge_t(bin_edge01(P.S - 1, P.S, step), tn, tf), eE = edge_t(bin_edge01(P.S, P.S, step), tn, tf);
+    mn = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
+    mx = __fmul_rn(__fadd_rn(eL, eE), 0.5f);
+    chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
+  }
+  // warp-aggregate when the whole warp sits in one chunk (the common case)
+  unsigned full = __activemask();
+  long long c0 = __shfl_sync(full, chunk, 0);
+  bool uniform = __all_sync(full, (!ok) || chunk == c0);
+  if (uniform) {
+    for (int s = 16; s > 0; s >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(full, mn, s));
+      mx = fmaxf(mx, __shfl_xor_sync(full, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0 && mn != INFINITY) {
+      // all values are >= 0, so the int ordering equals the float ordering
+      atomicMin((int*)(ws + 2 * c0), __float_as_int(mn));
+      atomicMax((int*)(ws + 2 * c0 + 1), __float_as_int(mx));
+    }
+  } else if (ok) {
+    atomicMin((int*)(ws + 2 * chunk), __float_as_int(mn));
+    atomicMax((int*)(ws + 2 * chunk + 1), __float_as_int(mx));
+  }
+}
+
+// ---- trilinear sdf + analytic gradient (w.r.t. grid coords) ------------------------------------------
+__device__ __forceinline__ void gather_sdf(const VolumeDev& v, const Taps& t, float& s, float& dgh, float& dgw,
+                                           float& dgd) {
+  int h0 = min(max(t.h0, 0), v.H - 1), h1 = min(max(t.h0 + 1, 0), v.H - 1);
+  int w0 = min(max(t.w0, 0), v.W - 1), w1 = min(max(t.w0 + 1, 0), v.W - 1);
+  int z0 = min(max(t.z0, 0), v.Z - 1), z1 = min(max(t.z0 + 1, 0), v.Z - 1);
+  const float* p00 = v.sdf + ((size_t)h0 * v.W + w0) * v.zpitch;
+  const float* p01 = v.sdf + ((size_t)h0 * v.W + w1) * v.zpitch;
+  const float* p10 = v.sdf + ((size_t)h1 * v.W + w0) * v.zpitch;
+  const float* p11 = v.sdf + ((size_t)h1 * v.W + w1) * v.zpitch;
+  float a000 = __ldg(p00 + z0), a001 = __ldg(p00 + z1);
+  float a010 = __ldg(p01 + z0), a011 = __ldg(p01 + z1);
+  float a100 = __ldg(p10 + z0), a101 = __ldg(p10 + z1);
+  float a110 = __ldg(p11 + z0), a111 = __ldg(p11 + z1);
+  float m00 = t.mh0 * t.mw0, m01 = t.mh0 * t.mw1, m10 = t.mh1 * t.mw0, m11 = t.mh1 * t.mw1;
+  a000 *= m00 * t.mz0; a001 *= m00 * t.mz1;
+  a010 *= m01 * t.mz0; a011 *= m01 * t.mz1;
+  a100 *= m10 * t.mz0; a101 *= m10 * t.mz1;
+  a110 *= m11 * t.mz0; a111 *= m11 * t.mz1;
+  float dz00 = a001 - a000, dz01 = a011 - a010, dz10 = a101 - a100, dz11 = a111 - a110;
+  float c00 = fmaf(t.fz, dz00, a000), c01 = fmaf(t.fz, dz01, a010);
+  float c10 = fmaf(t.fz, dz10, a100), c11 = fmaf(t.fz, dz11, a110);
+  float dw0 = c01 - c00, dw1 = c11 - c10;
+  float c0 = fmaf(t.fw, dw0, c00), c1 = fmaf(t.fw, dw1, c10);
+  float dz0 = fmaf(t.fw, dz01 - dz00, dz00), dz1 = fmaf(t.fw, dz11 - dz10, dz10);
+  dgh = c1 - c0;
+  s = fmaf(t.fh, dgh, c0);
+  dgw = fmaf(t.fh, dw1 - dw0, dw0);
+  dgd = fmaf(t.fh, dz1 - dz0, dz0);
+}
+
+// trilinear gather of `n` consecutive feature channels starting at `c0` (channel-last volume)
+template <int N>
+__device__ __forceinline__ void gather_feat(const VolumeDev& v, const Taps& t, int c0, float out[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int dh = k >> 2, dw = (k >> 1) & 1, dz = k & 1;
+    float wgt = (dh ? t.fh * t.mh1 : (1.f - t.fh) * t.mh0) * (dw ? t.fw * t.mw1 : (1.f - t.fw) * t.mw0) *
+                (dz ? t.fz * t.mz1 : (1.f - t.fz) * t.mz0);
+    int h = min(max(t.h0 + dh, 0), v.H - 1), w = min(max(t.w0 + dw, 0), v.W - 1), z = min(max(t.z0 + dz, 0), v.Z - 1);
+    const float* p = v.feat + (((size_t)h * v.W + w) * v.Z + z) * v.feat_pitch + c0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = fmaf(wgt, __ldg(p + i), out[i]);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+constexpr float kC0 = 0.28209479177387814f;  // sh_render.py:4
+constexpr int kMaxSem = 32;
+
+template <bool HAS_RGB, bool HAS_SEM>
+__global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+                                                           const float* __restrict__ bkgd_rand, float* __restrict__ depth,
+                                                           float* __restrict__ max_depth, long long* __restrict__ max_idx,
+                                                           float* __restrict__ acc_out, float* __restrict__ normal_vis,
+                                                           float* __restrict__ rgb_out, float* __restrict__ sem_out) {
+  long long lid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (lid >= R.ray_count) return;
+  long long gid = R.ray_begin + lid;
+  float o[3], d[3], nrm, tn, tf;
+  make_ray(R, gid, o, d, nrm);
+  slab(P, o, d, tn, tf);
+
+  const int S = P.S;
+  const float step = 1.0f / (float)S;
+  const float eps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (neus_head.py:431)
+  float T = 1.0f, acc = 0.f, dsum = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  float best = -INFINITY, best_mid = 0.f;
+  int best_i = 0;
+  float c_r = 0.f, c_g = 0.f, c_b = 0.f;
+  float sem[HAS_SEM ? kMaxSem : 1];
+  const int n_sem = HAS_SEM ? V.n_feat - 3 : 0;
+  if (HAS_SEM)
+    for (int i = 0; i < kMaxSem; ++i) sem[i] = 0.f;
+
+  float e0 = edge_t(bin_edge01(0, S, step), tn, tf);
+#pragma unroll 2
+  for (int s = 0; s < S; ++s) {
+    float e1 = edge_t(bin_edge01(s + 1, S, step), tn, tf);
+    float mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
+    float delta = __fsub_rn(e1, e0);
+    float tq = P.anchor_mid ? mid : e0;
+    e0 = e1;
+    float x = fmaf(d[0], tq, o[0]), y = fmaf(d[1], tq, o[1]), z = fmaf(d[2], tq, o[2]);
+    float kh, kw, kd;
+    float gh = axis_m2g(V.ax[0], y, kh), gw = axis_m2g(V.ax[1], x, kw), gd = axis_m2g(V.ax[2], z, kd);
+    Taps t = make_taps(V, gh, gw, gd);
+    float sdf, dgh, dgw, dgd;
+    gather_sdf(V, t, sdf, dgh, dgw, dgd);
+    float gx = dgw * kw, gy = dgh * kh, gz = dgd * kd;  // d sdf / d metre (x, y, z)
+    // NeuS alpha (upstream SDFField.get_alpha)
+    float tc = d[0] * gx + d[1] * gy + d[2] * gz;
+    float ic = -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
+    float half = ic * delta * 0.5f;
+    float pc = sigmoidf_acc((sdf - half) * P.inv_s);
+    float nc = sigmoidf_acc((sdf + half) * P.inv_s);
+    float alpha = fminf(fmaxf((pc - nc + 1e-5f) / (pc + 1e-5f), 0.f), 1.f);
+    float w = alpha * T;
+    T *= (1.0f - alpha + 1e-7f);
+    acc += w;
+    dsum = fmaf(w, mid, dsum);
+    float gn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);  // F.normalize eps
+    float wn = w / gn;
+    n0 = fmaf(wn, gx, n0); n1 = fmaf(wn, gy, n1); n2 = fmaf(wn, gz, n2);
+    // max-depth candidate (neus_head.py:430-438): first maximum of w / clamp(delta', eps), w := 0 where delta' < eps
+    float dl = delta / nrm;
+    float cand = (dl < eps ? 0.f : w) / fmaxf(dl, eps);
+    if (cand > best) { best = cand; best_i = s; best_mid = mid; }
+    if (HAS_RGB) {
+      float f[3];
+      gather_feat<3>(V, t, 0, f);
+      float r0 = f[0] * kC0, r1 = f[1] * kC0, r2 = f[2] * kC0;
+      if (P.sh_act == 0) { r0 = fmaxf(r0 + 0.5f, 0.f); r1 = fmaxf(r1 + 0.5f, 0.f); r2 = fmaxf(r2 + 0.5f, 0.f); }
+      else { r0 = sigmoidf_acc(r0); r1 = sigmoidf_acc(r1); r2 = sigmoidf_acc(r2); }
+      c_r = fmaf(w, r0, c_r); c_g = fmaf(w, r1, c_g); c_b = fmaf(w, r2, c_b);
+    }
+    if (HAS_SEM) {
+      // rendered semantics = sum_s w * softmax(logits) (bev_nerf.py:147-148 + SemanticRenderer)
+      float lg[kMaxSem];
+      float mx = -INFINITY;
+      for (int c = 0; c < n_sem; ++c) { float f1[1]; gather_feat<1>(V, t, 3 + c, f1); lg[c] = f1[0]; mx = fmaxf(mx, f1[0]); }
+      float den = 0.f;
+      for (int c = 0; c < n_sem; ++c) { lg[c] = expf(lg[c] - mx); den += lg[c]; }
+      float sc = w / den;
+      for (int c = 0; c < n_sem; ++c) sem[c] = fmaf(sc, lg[c], sem[c]);
+    }
+  }
+
+  long long chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
+  float lo = __ldg(ws + 2 * chunk), hi = __ldg(ws + 2 * chunk + 1);
+  if (depth) {
+    float dd = dsum / (acc + 1e-10f);
+    dd = fminf(fmaxf(dd, lo), hi);
+    depth[lid] = dd / nrm;
+  }
+  if (max_depth) max_depth[lid] = best_mid / nrm;
+  if (max_idx) max_idx[lid] = best_i;
+  if (acc_out) acc_out[lid] = acc;
+  if (normal_vis) {
+    normal_vis[3 * lid + 0] = (n0 + 1.0f) * 0.5f;
+    normal_vis[3 * lid + 1] = (n1 + 1.0f) * 0.5f;
+    normal_vis[3 * lid + 2] = (n2 + 1.0f) * 0.5f;
+  }
+  if (HAS_RGB && rgb_out) {
+    float b0, b1, b2;
+    if (P.bkgd_mode == 2) { b0 = bkgd_rand[3 * lid]; b1 = bkgd_rand[3 * lid + 1]; b2 = bkgd_rand[3 * lid + 2]; }
+    else { b0 = b1 = b2 = (P.bkgd_mode == 1) ? 1.f : 0.f; }
+    float rem = 1.0f - acc;
+    float r = fmaf(b0, rem, c_r), g = fmaf(b1, rem, c_g), b = fmaf(b2, rem, c_b);
+    if (P.eval_clamp) { r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); b = fminf(fmaxf(b, 0.f), 1.f); }
+    rgb_out[3 * lid] = r; rgb_out[3 * lid + 1] = g; rgb_out[3 * lid + 2] = b;
+  }
+  if (HAS_SEM && sem_out)
+    for (int c = 0; c < n_sem; ++c) sem_out[lid * n_sem + c] = sem[c];
+}
+
+__global__ void __launch_bounds__(256) field_query_kernel(VolumeDev V, const float* __restrict__ pts, long long n,
+                                                          float* __restrict__ sdf_out, float* __restrict__ grad_out,
+                                                          float* __restrict__ feat_out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  float kh, kw, kd;
+  float gh = axis_m2g(V.ax[0], y, kh), gw = axis_m2g(V.ax[1], x, kw), gd = axis_m2g(V.ax[2], z, kd);
+  Taps t = make_taps(V, gh, gw, gd);
+  float sdf, dgh, dgw, dgd;
+  gather_sdf(V, t, sdf, dgh, dgw, dgd);
+  if (sdf_out) sdf_out[i] = sdf;
+  if (grad_out) { grad_out[3 * i] = dgw * kw; grad_out[3 * i + 1] = dgh * kh; grad_out[3 * i + 2] = dgd * kd; }
+  if (feat_out)
+    for (int c = 0; c < V.n_feat; ++c) { float f1[1]; gather_feat<1>(V, t, c, f1); feat_out[i * V.n_feat + c] = f1[0]; }
+}
+
+}  // namespace so
+
+using namespace so;
+
+extern "C" int64_t so_render_workspace_floats(int64_t n_chunks) { return 2 * (n_chunks > 0 ? n_chunks : 1); }
+
+extern "C" int so_render_infer(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                               const float* cam_mats, const float* pix, const so_ray_desc* rd,
+                               const so_render_params* pr, const float* bkgd_rand, float* depth, float* max_depth,
+                               int64_t* max_idx, float* acc, float* normal_vis, float* rgb, float* sem,
+                               float* workspace, void* stream) {
+  if (!vol_sdf || !cam_mats || !rd || !pr || !workspace) return SO_ERR_INVALID_ARG;
+  int rc = validate_volume(vol_host);
+  if (rc) return rc;
+  if (rd->n_cam < 1 || rd->rays_per_cam < 1 || pr->num_samples < 1) return SO_ERR_INVALID_ARG;
+  if (!pix && (rd->nx < 1 || rd->ny < 1 || (int64_t)rd->nx * rd->ny != rd->rays_per_cam)) return SO_ERR_INVALID_ARG;
+  int64_t total = (int64_t)rd->n_cam * rd->rays_per_cam;
+  if (rd->ray_begin < 0 || rd->ray_count < 0 || rd->ray_begin + rd->ray_count > total) return SO_ERR_INVALID_ARG;
+  bool want_rgb = rgb != nullptr, want_sem = sem != nullptr;
+  if (want_rgb && (vol_host->n_feat < 3 || !vol_feat)) return SO_ERR_INVALID_ARG;
+  if (want_sem && (vol_host->n_feat <= 3 || !vol_feat || !want_rgb)) return SO_ERR_INVALID_ARG;
+  if (want_sem && vol_host->n_feat - 3 > kMaxSem) return SO_ERR_UNSUPPORTED;
+  if (pr->bkgd_mode == 2 && want_rgb && !bkgd_rand) return SO_ERR_INVALID_ARG;
+  if (pr->bkgd_mode < 0 || pr->bkgd_mode > 2 || pr->sh_act < 0 || pr->sh_act > 1) return SO_ERR_INVALID_ARG;
+  if (rd->ray_count == 0) return SO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  VolumeDev V = make_volume(*vol_host, vol_sdf, vol_feat);
+  RayDev R;
+  R.cam = cam_mats; R.pix = pix; R.n_cam = rd->n_cam; R.rays_per_cam = rd->rays_per_cam; R.nx = rd->nx > 0 ? rd->nx : 1;
+  R.sx = rd->sx; R.ox = rd->ox; R.sy = rd->sy; R.oy = rd->oy;
+  R.ray_begin = rd->ray_begin; R.ray_count = rd->ray_count; R.total = total;
+  R.chunk_len = rd->chunk_len > 0 ? rd->chunk_len : 0;
+  RenderDev P;
+  for (int a = 0; a < 3; ++a) { P.lo[a] = pr->aabb[a]; P.hi[a] = pr->aabb[3 + a]; }
+  P.near_clamp = pr->training ? pr->near_plane : 0.f;
+  P.S = pr->num_samples; P.inv_s = pr->inv_s; P.cos_anneal = pr->cos_anneal;
+  P.anchor_mid = pr->anchor_mid; P.sh_act = pr->sh_act; P.bkgd_mode = pr->bkgd_mode; P.eval_clamp = pr->training ? 0 : 1;
+
+  long long n_chunks = R.chunk_len > 0 ? ceil_div64(total, R.chunk_len) : 1;
+  bounds_init_kernel<<<(unsigned)ceil_div64(n_chunks, 256), 256, 0, st>>>(workspace, n_chunks);
+  bounds_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(R, P, workspace);
+  note_launch(2);
+  if ((rc = check_launch())) return rc;
+
+  unsigned grid = (unsigned)ceil_div64(rd->ray_count, 128);
+  long long* midx = reinterpret_cast<long long*>(max_idx);
+  if (want_sem)
+    render_infer_kernel<true, true><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
+  else if (want_rgb)
+    render_infer_kernel<true, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
+  else
+    render_infer_kernel<false, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_field_query(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                              const float* points, int64_t n, float* sdf, float* grad, float* feat, void* stream) {
+  if (!vol_sdf || !points || n < 0) return SO_ERR_INVALID_ARG;
+  int rc = validate_volume(vol_host);
+  if (rc) return rc;
+  if (feat && (vol_host->n_feat < 1 || !vol_feat)) return SO_ERR_INVALID_ARG;
+  if (n == 0) return SO_OK;
+  VolumeDev V = make_volume(*vol_host, vol_sdf, vol_feat);
+  field_query_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(V, points, n, sdf, grad, feat);
+  note_launch(1);
+  return check_launch();
+}

@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         f.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)

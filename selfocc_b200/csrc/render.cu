@@ -163,7 +163,22 @@ __device__ __forceinline__ void gather_feat(const VolumeDev& v, const Taps& t, i
   }
 }
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_acc(float x) {
+  float e = expf(-fabsf(x));
+  float s = 1.0f / (1.0f + e);
+  return x >= 0.f ? s : e * s;
+}
+
+// NeuS alpha = clip((Phi(prev) - Phi(next) + 1e-5) / (Phi(prev) + 1e-5), 0, 1) with Phi = sigmoid(inv_s * .),
+// prev = sdf - half, next = sdf + half (half <= 0).  The difference of the two CDFs is evaluated without
+// cancellation:  Phi(a) - Phi(b) = Phi(a) * Phi(-b) * (1 - exp(-(a - b))),  a - b = -2 * half * inv_s >= 0,
+// which keeps fp32 within rounding of the fp64 evaluation of the reference formula.
+__device__ __forceinline__ float neus_alpha(float sdf, float half, float inv_s) {
+  float a = (sdf - half) * inv_s, b = (sdf + half) * inv_s;
+  float pa = sigmoidf_acc(a);
+  float diff = pa * sigmoidf_acc(-b) * (-expm1f(2.0f * half * inv_s));
+  return fminf(fmaxf((diff + 1e-5f) / (pa + 1e-5f), 0.f), 1.f);
+}
 
 constexpr float kC0 = 0.28209479177387814f;  // sh_render.py:4
 constexpr int kMaxSem = 32;
@@ -211,10 +226,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     // NeuS alpha (upstream SDFField.get_alpha)
     float tc = d[0] * gx + d[1] * gy + d[2] * gz;
     float ic = -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
-    float half = ic * delta * 0.5f;
-    float pc = sigmoidf_acc((sdf - half) * P.inv_s);
-    float nc = sigmoidf_acc((sdf + half) * P.inv_s);
-    float alpha = fminf(fmaxf((pc - nc + 1e-5f) / (pc + 1e-5f), 0.f), 1.f);
+    float alpha = neus_alpha(sdf, ic * delta * 0.5f, P.inv_s);
     float w = alpha * T;
     T *= (1.0f - alpha + 1e-7f);
     acc += w;

@@ -31,26 +31,28 @@ class GridMeterMapping:
 
     # -- tensor maps (used for construction-time tables only; the hot path does this in-kernel) --
     @staticmethod
-    def _seg(v, a, b, ka, kb):
-        if kb is None:
-            return v * ka
-        return torch.where(v > a, b + (v - a) * kb, v * ka)
+    def _seg(v, a0, b0, a1, b1):
+        """Two-segment piecewise-linear map a -> b.  Operation order (divide, then multiply) follows
+        mappings.py:53-60 / :101-109 so construction-time tables are bit-identical to the reference's."""
+        inner = v / a0 * b0
+        if a1 <= 0:
+            return inner
+        return torch.where(v > a0, b0 + (v - a0) / a1 * b1, inner)
 
     def _axis_g2m(self, k, g):
         a = self._ax[k]
-        c = g - a['offset']
-        s0, s1 = a['size']
-        r0, r1 = a['rng']
-        m = self._seg(c.abs(), s0, r0, r0 / s0, (r1 / s1) if s1 > 0 else None)
-        return torch.sign(c) * m + a['start']
+        c = g - a['offset'] if a['offset'] != 0 else g
+        m = self._seg(c.abs(), a['size'][0], a['rng'][0], a['size'][1], a['rng'][1])
+        m = torch.sign(c) * m
+        return m + a['start'] if k == 'd' else m
 
     def _axis_m2g(self, k, m):
         a = self._ax[k]
-        c = m - a['start']
-        s0, s1 = a['size']
-        r0, r1 = a['rng']
-        g = self._seg(c.abs(), r0, s0, s0 / r0, (s1 / r1) if s1 > 0 else None)
-        return torch.sign(c) * g + a['offset']
+        c = m - a['start'] if k == 'd' else m
+        g = torch.sign(c) * self._seg(c.abs(), a['rng'][0], a['size'][0], a['rng'][1], a['size'][1])
+        if a['offset'] != 0:
+            g = g + a['size'][0] + a['size'][1]
+        return g
 
     def grid2meter(self, grid):
         """grid[..., (h, w[, d])] -> metres[..., (x, y[, z])]"""

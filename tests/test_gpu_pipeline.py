@@ -1,0 +1,150 @@
+"""GPU parity of the whole hot path through the reference-facing module API:
+TPVQueryLifter -> TPVFormerEncoder -> NeuSHead.prepare/render/forward_occ vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from selfocc_b200 import synth, configs
+from selfocc_b200.registry import build_head
+import selfocc_b200.segmentor  # noqa: F401
+
+
+def _setup(color_dims=0, return_sem=False, seed=0):
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    torch.manual_seed(seed)
+    margs, rng = synth.small_mapping(8, 4, rng=20.0, z0=-2.0, z1=4.0)
+    cfg = configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=6, num_layers=2, num_points_cross=(6, 6, 4),
+                                  num_points_self=4, num_samples=48, ray_number=(9, 16), ray_img_size=(90, 160),
+                                  color_dims=color_dims, return_sem=return_sem)
+    model = build_head(cfg)
+    model.encoder.init_weights()
+    # perturb the zero-initialised offset / weight projections so the test is not the trivial uniform-softmax case
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'sampling_offsets.weight' in n or 'attention_weights.weight' in n:
+                p.normal_(0, 0.05)
+        model.lifter.tpv_hw.mul_(0.5); model.lifter.tpv_zh.mul_(0.5); model.lifter.tpv_wz.mul_(0.5)
+        model.head.model.field.deviation_network.variance.fill_(0.25)
+    model.eval()
+    l2i, i2l = synth.camera_rig(synth.NUSC_YAWS, f=126.6, cx=80., cy=45., height=0.5, radius=0.2)
+    metas = [dict(lidar2img=list(l2i), img2lidar=list(i2l), img_shape=(90, 160))]
+    feats = [torch.randn(1, 6, 96, h, w) for h, w in [(12, 20), (6, 10), (3, 5), (2, 3)]]
+    return model, cfg, margs, rng, metas, feats, torch.tensor(l2i, dtype=torch.float32), torch.tensor(i2l, dtype=torch.float32)
+
+
+def _oracle_planes(model, cfg, margs, feats, l2i):
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import lifting as ol
+    p = {k[len('encoder.'):]: v.detach().cpu().double() for k, v in model.state_dict().items() if k.startswith('encoder.')}
+    mref = GridMeterMappingRef(**margs)
+    enc = cfg['encoder']
+    ocfg = dict(num_freqs=[12] * 3, tot_range=enc['positional_encoding']['tot_range'], num_points_cross=enc['num_points_cross'],
+                num_points_self=enc['num_points_self'][0], num_layers=enc['num_layers'], num_heads=6, num_cams=6)
+    planes = [model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz]
+    planes = [q.detach().cpu().double() for q in planes]
+    # fp64 oracle: positional features/tables are fp32 constants promoted to fp64
+    out = ol.tpv_encoder_ref(_P64(p), mref, planes, [f.double() for f in feats], l2i[None], (90, 160), ocfg)
+    return mref, out
+
+
+class _P64(dict):
+    """parameter dict whose fp32 constants get promoted when they meet fp64 activations."""
+    def __init__(self, d):
+        super().__init__(d)
+
+
+def test_encoder_matches_oracle():
+    model, cfg, margs, rng, metas, feats, l2i, i2l = _setup()
+    dev = torch.device('cuda:0')
+    model.to(dev)
+    import oracle.lifting as ol
+    # run the oracle in fp64 (tables stay fp32-valued): monkeypatch-free -- the oracle promotes via torch type promotion
+    orig = ol.tpv_pos_features
+    ol.tpv_pos_features = lambda *a, **k: [f.double() for f in orig(*a, **k)]
+    orig_ps = ol.point_sampling_ref
+    ol.point_sampling_ref = lambda r, m, s: tuple(t.double() if t.dtype.is_floating_point else t for t in orig_ps(r, m, s))
+    orig_cv = ol.cross_view_ref_points
+    ol.cross_view_ref_points = lambda *a: orig_cv(*a).double()
+    try:
+        mref, ref = _oracle_planes(model, cfg, margs, feats, l2i)
+    finally:
+        ol.tpv_pos_features, ol.point_sampling_ref, ol.cross_view_ref_points = orig, orig_ps, orig_cv
+    with torch.no_grad():
+        res = model.lifter(ms_img_feats=[f.to(dev) for f in feats])
+        out = model.encoder(representation=res['representation'], ms_img_feats=[f.to(dev) for f in feats], metas=metas)
+    for a, b in zip(out['representation'], ref):
+        err = (a.cpu() - b.float()).abs().max().item()
+        print('encoder plane max abs err %.3e (|x| max %.2f)' % (err, b.abs().max().item()))
+        assert err < 2e-4
+    # the autograd (training) path of the same modules must agree with the fused inference path
+    res2 = model.lifter(ms_img_feats=[f.to(dev) for f in feats])
+    out2 = model.encoder(representation=res2['representation'], ms_img_feats=[f.to(dev) for f in feats], metas=metas)
+    assert out2['representation'][0].requires_grad
+    for a, b in zip(out['representation'], out2['representation']):
+        assert torch.allclose(a, b.detach(), atol=2e-5, rtol=1e-5)
+    out2['representation'][0].sum().backward()
+    assert model.lifter.tpv_hw.grad is not None and torch.isfinite(model.lifter.tpv_hw.grad).all()
+
+
+@pytest.mark.parametrize('color_dims,return_sem,batch', [(0, False, 0), (7, True, 300)])
+def test_head_prepare_render_matches_oracle(color_dims, return_sem, batch):
+    model, cfg, margs, rng, metas, feats, l2i, i2l = _setup(color_dims, return_sem)
+    dev = torch.device('cuda:0')
+    model.to(dev)
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender, rays as orays, metric
+    mref = GridMeterMappingRef(**margs)
+    planes = [0.5 * torch.randn_like(p) for p in (model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz)]
+    with torch.no_grad():
+        model.head.prepare(representation=planes, metas=metas)
+        out = model.head.render(metas=metas, batch=batch)
+    f = model.head.model.field
+    w1, b1, w2, b2 = (t.detach().cpu().double() for t in (f.density_net[1].weight, f.density_net[1].bias,
+                                                         f.density_net[3].weight, f.density_net[3].bias))
+    H, W, Z = mref.size_h, mref.size_w, mref.size_d
+    vol = orender.tpv_decode_ref(*[p[0].cpu().double() for p in planes], (H, W, Z), w1, b1, w2, b2)
+    pix = orays.fixed_ray_grid([9, 16], [90, 160])
+    assert torch.equal(out['ms_rays'].cpu(), pix)                         # ray order / pixel coords: bit exact
+    origin, direction = orays.img2lidar_rays(i2l[None], pix)
+    inv_s = float(f.deviation_network.get_variance())
+    ref = orender.head_render_ref(vol, mref, origin.double(), direction.double(), rng, inv_s, batch=batch, S=48,
+                                  color_dims=3 if color_dims else 0, bkgd='white')
+    d, dref = out['ms_depths'][0].cpu(), ref['depth'].float()
+    assert d.shape == (1, 6, 144)
+    rel = ((d - dref).abs() / dref.abs().clamp_min(1e-6)).max().item()
+    absrel = float(metric.cal_depth_metric_ref(d.reshape(-1).double(), dref.reshape(-1).double().clamp(1e-3, 80))['abs_rel'])
+    print('pipeline depth max rel err %.3e, AbsRel vs oracle %.3e' % (rel, absrel))
+    assert rel < 1e-4 and absrel < 1e-5
+    assert torch.allclose(out['ms_accs'][0].cpu(), ref['acc'].float(), atol=2e-5)
+    md = out['ms_max_depths'][0].cpu()
+    agree = torch.isclose(md, ref['max_depth'].float(), rtol=1e-5, atol=1e-6)
+    assert agree.float().mean() > 0.98
+    if color_dims:
+        assert torch.allclose(out['ms_colors'][0].cpu(), ref['rgb'].float(), atol=5e-5)
+        assert torch.allclose(out['sem'][0].cpu(), ref['sem'].float(), atol=5e-5)
+    else:
+        assert out['ms_colors'][0].shape[-1] == 0
+
+
+def test_forward_occ_matches_oracle():
+    model, cfg, margs, rng, metas, feats, l2i, i2l = _setup(7, True)
+    dev = torch.device('cuda:0')
+    model.to(dev)
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender
+    mref = GridMeterMappingRef(**margs)
+    planes = [0.5 * torch.randn_like(p) for p in (model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz)]
+    out = model.head.forward_occ(representation=planes, metas=metas, aabb=rng, resolution=1.3)
+    f = model.head.model.field
+    w1, b1, w2, b2 = (t.detach().cpu().double() for t in (f.density_net[1].weight, f.density_net[1].bias,
+                                                         f.density_net[3].weight, f.density_net[3].bias))
+    vol = orender.tpv_decode_ref(*[p[0].cpu().double() for p in planes], (mref.size_h, mref.size_w, mref.size_d), w1, b1, w2, b2)
+    sdf, sem, xyz = orender.uniform_sdf_ref(vol, mref, rng, 1.3)
+    assert out['sdf'].shape == sdf.shape
+    assert torch.allclose(out['xyz'].cpu(), xyz, atol=1e-5)
+    assert torch.allclose(out['sdf'].cpu(), sdf.float(), atol=3e-5)
+    assert torch.allclose(out['logits'].cpu(), sem.float(), atol=3e-5)
+    assert out['sem'].dtype == torch.int64

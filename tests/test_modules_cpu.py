@@ -1,0 +1,83 @@
+"""CPU: registry / constructor / state_dict contract of the drop-in modules (no kernel calls)."""
+import torch
+import pytest
+from selfocc_b200 import synth, configs
+from selfocc_b200.registry import MODELS, build_head
+import selfocc_b200.segmentor  # noqa: F401  (registers everything)
+
+
+def _small_cfg(**kw):
+    margs, rng = synth.small_mapping(6, 3)
+    return configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=3, num_layers=2, num_points_cross=(5, 5, 3),
+                                   num_points_self=4, num_samples=32, ray_number=(6, 10), ray_img_size=(90, 160), **kw)
+
+
+def test_registry_builds_reference_style_config():
+    model = build_head(_small_cfg())
+    for name in ('TPVQueryLifter', 'TPVFormerEncoder', 'TPVFormerLayer', 'TPVPositionalEncoding', 'CrossViewHybridAttention',
+                 'TPVCrossAttention', 'BEVCrossAttention', 'BEVDeformableAttention', 'NeuSHead'):
+        assert name in MODELS
+    keys = set(model.state_dict().keys())
+    # checkpoint key names of the reference modules (state-dict keys are part of the boundary)
+    for k in ('lifter.tpv_hw', 'lifter.tpv_zh', 'lifter.tpv_wz', 'encoder.level_embeds', 'encoder.cams_embeds',
+              'encoder.positional_encoding.position_layer_hw.weight',
+              'encoder.layers.0.attentions.0.sampling_offsets.weight', 'encoder.layers.0.attentions.0.output_proj.bias',
+              'encoder.layers.1.attentions.1.attn_zh.deformable_attention.value_proj.weight',
+              'encoder.layers.1.attentions.1.attn_wz.output_proj.weight', 'encoder.layers.0.ffns.0.layers.0.0.weight',
+              'encoder.layers.0.ffns.0.layers.1.bias', 'encoder.layers.1.norms.2.weight',
+              'head.model.field.density_net.1.weight', 'head.model.field.density_net.3.bias',
+              'head.model.field.deviation_network.variance'):
+        assert k in keys, k
+    # non-persistent buffers (reference registers them with persistent=False)
+    assert not any('ref_3d' in k or 'freq_feat' in k or 'cross_view_ref_points' in k for k in keys)
+    enc = model.encoder
+    assert enc.ref_3d_hw.shape == (3, 13 * 13, 3) and enc.ref_3d_zh.shape == (5, 4 * 13, 3)
+    assert enc.cross_view_ref_points.shape == (13 * 13 + 2 * 4 * 13, 3, 4, 2)
+
+
+def test_tables_match_oracle():
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import lifting as ol
+    margs, rng = synth.small_mapping(6, 3)
+    model = build_head(_small_cfg())
+    mref = GridMeterMappingRef(**margs)
+    for a, b in zip((model.encoder.ref_3d_hw, model.encoder.ref_3d_zh, model.encoder.ref_3d_wz), ol.ref_3d_tables(mref, [5, 5, 3])):
+        assert torch.equal(a, b)
+    assert torch.equal(model.encoder.cross_view_ref_points, ol.cross_view_ref_points(13, 13, 4, [4, 4, 4]))
+    feats = ol.tpv_pos_features(mref, [12] * 3, rng)
+    pe = model.encoder.positional_encoding
+    for a, b in zip((pe.hw_freq_feat, pe.zh_freq_feat, pe.wz_freq_feat), feats):
+        assert torch.equal(a, b)
+    pts = (torch.rand(50, 3) - 0.5) * 30
+    assert torch.equal(model.encoder.mapping.meter2grid(pts, True), mref.meter2grid(pts, True))
+
+
+def test_deformable_init_matches_reference_recipe():
+    model = build_head(_small_cfg())
+    sa = model.encoder.layers[0].attentions[0]
+    assert torch.count_nonzero(sa.sampling_offsets.weight) == 0 and torch.count_nonzero(sa.attention_weights.weight) == 0
+    b = sa.sampling_offsets.bias.view(6, 3, 4, 2)
+    assert torch.allclose(b[0, 0, :, 0], torch.tensor([1., 2., 3., 4.]))      # mmcv MSDA: point i scaled by i+1
+    ca = model.encoder.layers[0].attentions[1].attn_hw.deformable_attention
+    assert torch.allclose(ca.sampling_offsets.bias.view(6, 4, 3, 2)[0, :, :, 0], torch.ones(4, 3))  # no scaling (:238-239)
+
+
+def test_fork_only_options_are_rejected():
+    cfg = _small_cfg()['head']
+    cfg.pop('type')
+    from selfocc_b200.head import NeuSHead
+    for k, v in (('anneal_aabb', True), ('disp_sampler', True), ('num_samples_importance', 64), ('use_numerical_gradients', True)):
+        with pytest.raises(NotImplementedError):
+            NeuSHead(**{**cfg, k: v})
+    with pytest.raises(NotImplementedError):
+        NeuSHead(**{**cfg, 'mapping_args': {**cfg['mapping_args'], 'nonlinear_mode': 'linear_upscale'}})
+
+
+def test_ray_sampler_grid_equals_table(golden):
+    import numpy as np
+    from selfocc_b200.head import RaySampler
+    rs = RaySampler('fixed', [6, 10], [90, 160])
+    assert torch.equal(rs(), torch.from_numpy(golden['rays_fixed_6x10_90x160']))
+    np.random.seed(123)
+    rc = RaySampler('cellular', [6, 10], [90, 160], ray_upper_crop=8)
+    assert torch.allclose(rc(), torch.from_numpy(golden['rays_cell_6x10_90x160']), atol=1e-5)

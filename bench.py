@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- rendered rays/second of the SelfOcc hot path on B200 (see DESIGN.md "Measurement").
+
+A step = ONE pass of the hot path over one synthetic 6-camera frame:
+    TPVQueryLifter -> TPVFormerEncoder (4 layers of self + image cross attention) -> NeuSHead.prepare
+    (TPV -> decoded volume) -> NeuSHead.render (6 x 900 x 1600 rays x 256 samples -> depth, max-depth, acc, normal)
+i.e. BASELINE.json configs[2] ("nuScenes novel-depth 900x1600 full-res render"), the configuration the
+metric "rendered rays/sec (6-cam 900x1600)" is quoted on.  The image backbone (third-party cuDNN ResNet/FPN) is
+outside the hot path: the step starts from synthetic FPN features.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --gpus N ...            # the CPU oracle port (the reference is not installable)
+
+N > 1 (torchrun): data-parallel frames exactly like the reference's DDP evaluation -- rank r lifts and renders
+its own frame -- plus the north-star's single all_gather of the rendered maps; per-GPU work is fixed (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (ray grid per camera, image size, FPN input (h, w) the level shapes derive from)
+    'nuscenes_novel_depth_900x1600': dict(ray_number=(900, 1600), ray_img_size=(900, 1600), fpn_hw=(768, 1600)),
+    'nuscenes_depth_450x800': dict(ray_number=(450, 800), ray_img_size=(900, 1600), fpn_hw=(896, 1600)),
+    'tiny': dict(ray_number=(32, 32), ray_img_size=(900, 1600), fpn_hw=(128, 256)),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='nuscenes_novel_depth_900x1600', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ synthetic frame
+def make_frame(workload, seed):
+    """Synthetic inputs of one frame: FPN features ~ N(0,1), the 6-camera nuScenes-like rig."""
+    from selfocc_b200 import synth
+    w = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(seed)
+    shapes = synth.fpn_level_shapes(w['fpn_hw'][0] // 2 * 2, w['fpn_hw'][1])
+    feats = [torch.randn(1, 6, 96, h, ww, generator=g) for h, ww in shapes]
+    l2i, i2l = synth.camera_rig()
+    metas = [dict(lidar2img=list(l2i), img2lidar=list(i2l), img_shape=(w['ray_img_size'][0], w['ray_img_size'][1]))]
+    return feats, metas, shapes
+
+
+def build_model(workload, device):
+    from selfocc_b200 import configs
+    from selfocc_b200.registry import build_head
+    import selfocc_b200.segmentor  # noqa: F401
+    w = WORKLOADS[workload]
+    torch.manual_seed(0)
+    cfg = configs.hot_path_config(ray_number=w['ray_number'], ray_img_size=w['ray_img_size'], return_max_depth=True)
+    model = build_head(cfg)
+    model.encoder.init_weights()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        for n, p in model.named_parameters():       # "stress" init of SURVEY 8d: non-trivial offsets / softmax
+            if 'sampling_offsets.weight' in n or 'attention_weights.weight' in n:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+        for p in (model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz):
+            p.mul_(0.1)
+        model.head.model.field.deviation_network.variance.fill_(0.3)
+    return model.eval().to(device), cfg
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from selfocc_b200 import _lib
+    from selfocc_b200.dist import all_gather_rays
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node == --gpus'
+    _lib.load()
+    model, cfg = build_model(args.workload, dev)
+    feats_h, metas, shapes = make_frame(args.workload, seed=100 + rank)
+    feats_h = [f.pin_memory() for f in feats_h]
+    feats_d = [f.to(dev) for f in feats_h]
+    import numpy as np
+    to_dev = lambda k: torch.as_tensor(np.asarray(metas[0][k]), dtype=torch.float32, device=dev)
+    metas_d = [dict(lidar2img=to_dev('lidar2img'), img2lidar=to_dev('img2lidar'), img_shape=metas[0]['img_shape'])]
+    n_cam, n_ray = 6, model.head.ray_sampler.ray_number
+    rays_per_frame = n_cam * n_ray
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    @torch.no_grad()
+    def step(feats, m):
+        r = model.lifter(ms_img_feats=feats)
+        r = model.encoder(representation=r['representation'], ms_img_feats=feats, metas=m)
+        model.head.prepare(representation=r['representation'], metas=m)
+        return model.head.render(metas=m, batch=0)
+
+    def gather(out):
+        if world == 1:
+            return out['ms_depths'][0]
+        packed = torch.stack([out['ms_depths'][0].reshape(-1), out['ms_max_depths'][0].reshape(-1)], -1)
+        return all_gather_rays(packed, world * rays_per_frame)     # the one collective (frames are equal-sized slices)
+
+    def timed(fn, K, W, sampler=None):
+        for _ in range(W):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = []
+        l0 = _lib.launch_count()
+        _lib.profile_reset()
+        for _ in range(K):
+            flush.zero_()                                          # evict L2 between timed steps (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)               # max over ranks
+        return float(t.item()), _lib.launch_count() - l0, clocks
+
+    K, W = args.steps, max(args.warmup, 3)
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler)
+    prof = _lib.profile_read()
+    ms_per_step = total_ms / K
+    value = world * rays_per_frame / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step through the public module API with HOST inputs / outputs inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        out_h = torch.empty(2, rays_per_frame, dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            fd = [f.to(dev, non_blocking=True) for f in feats_h]     # H2D of this step's inputs (pinned)
+            out = step(fd, metas)                                    # numpy metas: matrices uploaded per call like the reference
+            out_h[0].copy_(out['ms_depths'][0].reshape(-1), non_blocking=True)
+            out_h[1].copy_(out['ms_max_depths'][0].reshape(-1), non_blocking=True)
+            return gather(out) if world > 1 else None
+        _lib.profile_enable(False)
+        e_ms, _, _ = timed(step_e2e, K, W)
+        h2d = sum(f.numel() * 4 for f in feats_h) + 2 * 6 * 16 * 4
+        e2e = {'value': world * rays_per_frame / (e_ms / K * 1e-3), 'unit': 'rays/s', 'ms_per_step': e_ms / K,
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out_h.numel() * 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    r_ms, r_calls = prof.get('render_infer', (0.0, 0))
+    d = model.head.model.field.desc
+    vol_bytes = d.H * d.W * d.zpitch * 4
+    bytes_per_ray = 4 + 4 + 4 + 12            # depth, max_depth, acc, normal_vis actually written; rays are generated in-kernel
+    alg_bytes = rays_per_frame * bytes_per_ray + vol_bytes
+    dur = (r_ms / max(r_calls, 1)) * 1e-3
+    achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
+    flop_per_ray = 256 * 150.0                # SURVEY 8d estimate: ~150 flop per sample
+    roofline = {'kernel': 'render_infer_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': 'measured' if peaks else 'fallback',
+                'launch_ms': dur * 1e3, 'algorithmic_bytes_per_launch': alg_bytes,
+                'note': 'inference render is ALU/L1-gather bound by construction (~600 flop/B, SURVEY 8d caveat): '
+                        'fp32 throughput estimate %.1f TFLOP/s' % (rays_per_frame * flop_per_ray / dur / 1e12 if dur > 0 else 0)}
+    breakdown = {k: round(v[0] / K, 4) for k, v in prof.items()}
+    line = {'metric': 'rendered rays/sec (6-cam 900x1600)', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
+            'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'impl': 'b200',
+            'config': {'workload': args.workload, 'rays_per_frame': rays_per_frame, 'samples_per_ray': 256,
+                       'tpv': '257x257x31x96', 'fpn_levels': shapes, 'encoder_layers': 4,
+                       'frames_per_step': world, 'parallelism': 'dp%d frames + 1 all_gather' % world,
+                       'l2_flush_between_steps': True},
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+            'kernel_ms_per_step': breakdown}
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_reference(args.workload, steps=1, warmup=0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(workload, steps, warmup, full=False):
+    """The reference's CPU PyTorch path = the oracle port (the reference itself cannot be installed: mmcv / sdfstudio fork
+    absent).  Bounded sample, linearly extrapolated to the frame:
+      lift   : ONE of the 4 encoder layers at full size, x4        (measured once, outside the timed steps)
+      decode : full-size TPV decode                                 (measured once)
+      render : 1 camera x 45x80 rays of 6 x 900 x 1600, 256 samples, full 257x257x31 volume, reference-style chunk loop
+               with the CPU max-depth step                          (every step)
+    value = rays_per_frame / (t_lift + t_decode + t_render * scale)."""
+    import numpy as np
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import lifting as ol, render as orender, rays as orays
+    from selfocc_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    w = WORKLOADS[workload]
+    feats, metas, shapes = make_frame(workload, seed=100)
+    mref = GridMeterMappingRef(**synth.NUSC_MAPPING)
+    H, W, Z = mref.size_h, mref.size_w, mref.size_d
+    g = torch.Generator().manual_seed(0)
+    rays_per_frame = 6 * w['ray_number'][0] * w['ray_number'][1]
+    tiny = workload == 'tiny'
+    # --- fixed part, measured once
+    C = 96
+    planes = [0.1 * torch.randn(1, n, C, generator=g) for n in (H * W, Z * H, W * Z)]
+    t0 = time.perf_counter()
+    p = _random_encoder_params(C, g)
+    l2i = torch.tensor(np.asarray(metas[0]['lidar2img']), dtype=torch.float32)
+    cfg = dict(num_freqs=[12] * 3, tot_range=synth.NUSC_RANGE, num_points_cross=[48, 48, 8], num_points_self=12, num_layers=1,
+               num_heads=6, num_cams=6)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ol.tpv_encoder_ref(p, mref, planes, feats, l2i[None], metas[0]['img_shape'], cfg)
+    t_lift = (time.perf_counter() - t0) * 4
+    w1, b1, w2, b2 = synth.random_mlp(C, 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        vol = orender.tpv_decode_ref(planes[0][0], planes[1][0], planes[2][0], (H, W, Z), w1, b1, w2, b2)
+    t_decode = time.perf_counter() - t0
+    # --- per-step bounded render sample
+    ny, nx = (8, 8) if tiny else (45, 80)
+    pix = orays.fixed_ray_grid([ny, nx], list(w['ray_img_size']))
+    i2l = torch.tensor(np.asarray(metas[0]['img2lidar']), dtype=torch.float32)[None, :1]
+    origin, direction = orays.img2lidar_rays(i2l, pix)
+    scale = rays_per_frame / (ny * nx)
+
+    def render_sample():
+        t0 = time.perf_counter()
+        orender.head_render_ref(vol, mref, origin, direction, synth.NUSC_RANGE, 20.0, batch=90000, S=256)
+        return time.perf_counter() - t0
+    for _ in range(warmup):
+        render_sample()
+    ts = [render_sample() for _ in range(max(steps, 1))]
+    t_r = sum(ts) / len(ts)
+    frame_s = t_lift + t_decode + t_r * scale
+    return {'value': rays_per_frame / frame_s, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': 'oracle port (reference not installable): 1 of 4 encoder layers x4 (%.1fs) + full decode (%.1fs) + '
+                      'render of 1 cam x %dx%d rays x 256 samples (%.2fs) scaled x%.0f to %d rays'
+                      % (t_lift, t_decode, ny, nx, t_r, scale, rays_per_frame),
+            'ms_per_step_extrapolated': frame_s * 1e3, 'threads': torch.get_num_threads()}
+
+
+def _random_encoder_params(C, g):
+    """Parameter dict for one oracle encoder layer (state_dict key names of the reference modules)."""
+    p = {}
+
+    def lin(key, o, i, s=0.05):
+        p[key + '.weight'] = s * torch.randn(o, i, generator=g)
+        p[key + '.bias'] = s * torch.randn(o, generator=g)
+    for n in ('hw', 'zh', 'wz'):
+        lin('positional_encoding.position_layer_' + n, C, 48)
+    p['cams_embeds'] = torch.randn(6, C, generator=g)
+    p['level_embeds'] = torch.randn(4, C, generator=g)
+    a = 'layers.0.attentions.0.'
+    lin(a + 'sampling_offsets', 6 * 3 * 12 * 2, C); lin(a + 'attention_weights', 6 * 3 * 12, C)
+    lin(a + 'value_proj', C, C); lin(a + 'output_proj', C, C)
+    for n, D in (('attn_hw', 8), ('attn_zh', 48), ('attn_wz', 48)):
+        b = 'layers.0.attentions.1.%s.' % n
+        lin(b + 'deformable_attention.sampling_offsets', 6 * 4 * D * 2, C)
+        lin(b + 'deformable_attention.attention_weights', 6 * 4 * D, C)
+        lin(b + 'deformable_attention.value_proj', C, C)
+        lin(b + 'output_proj', C, C)
+    lin('layers.0.ffns.0.layers.0.0', 2 * C, C); lin('layers.0.ffns.0.layers.1', C, 2 * C)
+    for i in range(3):
+        p['layers.0.norms.%d.weight' % i] = torch.ones(C)
+        p['layers.0.norms.%d.bias' % i] = torch.zeros(C)
+    return p
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return                                     # rank 0 alone runs the CPU arm
+    K, W = args.steps, args.warmup
+    t0 = time.perf_counter()
+    cb = cpu_reference(args.workload, steps=min(K, 3), warmup=min(W, 1))
+    w = WORKLOADS[args.workload]
+    line = {'metric': 'rendered rays/sec (6-cam 900x1600)', 'value': cb['value'], 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': K, 'warmup': W, 'ms_per_step': cb['ms_per_step_extrapolated'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': args.workload, 'rays_per_frame': 6 * w['ray_number'][0] * w['ray_number'][1],
+                       'samples_per_ray': 256, 'tpv': '257x257x31x96'},
+            'cpu_baseline': cb, 'e2e': {'value': cb['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'wall_s': time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    run_reference(a) if a.impl == 'reference' else run_b200(a)

@@ -40,6 +40,16 @@ const char* so_error_string(int code);
  * gpu_launches claim is read from here). */
 int64_t so_launch_count(void);
 
+/* Optional per-kernel device timing (used by bench.py for the roofline line).  When enabled, the entry
+ * points bracket their dominant kernel with cudaEventRecord on the launch stream.  Tags:
+ * 0 render_infer, 1 tpv_decode, 2 tpv_cross_attn, 3 tpv_self_attn, 4 msda_forward, 5 msda_backward,
+ * 6 render_train_fwd, 7 render_train_bwd.  so_profile_elapsed_ms returns the SUM over the calls since
+ * the last so_profile_reset (the caller must have synchronised the stream) and the call count. */
+#define SO_PROF_NUM_TAGS 8
+int so_profile_enable(int on);
+int so_profile_reset(void);
+int so_profile_elapsed_ms(int tag, float* total_ms_host, int32_t* calls_host);
+
 /* ---------------------------------------------------------------------------------------
  * Grid <-> metre mapping, one axis.  Restates LinearMapping.meter2grid
  * (reference model/encoder/bevformer/mappings.py:97-150):

@@ -48,6 +48,9 @@ SIGNATURES = {
     'so_last_cuda_error': (C.c_int, []),
     'so_error_string': (C.c_char_p, [C.c_int]),
     'so_launch_count': (C.c_int64, []),
+    'so_profile_enable': (C.c_int, [C.c_int]),
+    'so_profile_reset': (C.c_int, []),
+    'so_profile_elapsed_ms': (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     'so_tpv_decode': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _P, _P, _P]),
     'so_render_workspace_floats': (C.c_int64, [_L]),
     'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
@@ -100,3 +103,28 @@ def check(code, what):
 
 def launch_count():
     return int(load().so_launch_count())
+
+
+PROF_TAGS = ('render_infer', 'tpv_decode', 'tpv_cross_attn', 'tpv_self_attn', 'msda_forward', 'msda_backward',
+             'render_train_fwd', 'render_train_bwd')
+
+
+def profile_enable(on=True):
+    load().so_profile_enable(int(on))
+    load().so_profile_reset()
+
+
+def profile_reset():
+    load().so_profile_reset()
+
+
+def profile_read():
+    """{tag: (total_ms, calls)} since the last reset; the stream must be synchronised first."""
+    lib = load()
+    out = {}
+    for i, t in enumerate(PROF_TAGS):
+        ms, n = C.c_float(0), C.c_int32(0)
+        check(lib.so_profile_elapsed_ms(i, C.byref(ms), C.byref(n)), 'so_profile_elapsed_ms')
+        if n.value:
+            out[t] = (ms.value, n.value)
+    return out

@@ -21,6 +21,15 @@ inline int check_launch() { return check_cuda(cudaGetLastError()); }
 
 constexpr int kNumSMs = 148;  // B200
 
+// Device-time bracket around the dominant kernel of an entry point (no-op unless so_profile_enable(1)).
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+struct ProfScope {
+  int tag; cudaStream_t st;
+  ProfScope(int t, cudaStream_t s) : tag(t), st(s) { prof_begin(tag, st); }
+  ~ProfScope() { prof_end(tag, st); }
+};
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- metre -> grid, one axis (mappings.py:97-150).  Device copy of so_axis_map with the two slopes

@@ -14,7 +14,6 @@ namespace so {
 
 constexpr int kRows = 128;      // voxels per CTA
 constexpr int kThreads = 256;
-constexpr int kMaxC = 128;
 constexpr int kMaxOut = 32;
 
 __device__ __forceinline__ float softplus_fast(float x) {
@@ -143,6 +142,7 @@ int launch_decode(const float* hw, const float* zh, const float* wz, const float
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div64((int64_t)d->W * d->Z, kRows), (unsigned)d->H);
+  ProfScope prof(1, st);
   tpv_decode_kernel<C><<<grid, kThreads, smem, st>>>(hw, zh, wz, w1, b1, w2, b2, d->H, d->W, d->Z, d->zpitch,
                                                        1 + d->n_feat, d->feat_pitch, vol_sdf, vol_feat);
   note_launch(1);

@@ -372,6 +372,7 @@ extern "C" int so_msda_forward(const float* value, const int64_t* spatial_shapes
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   long long threads = (long long)B * Nq * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
+  ProfScope prof(4, st);
   SO_DISPATCH_DH(Dh, (msda_forward_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, out, B, Nv, Hd, Nq, L, P)),
                  (msda_forward_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, out, B, Nv, Hd, Nq, L, P)));
   note_launch(1);
@@ -393,6 +394,7 @@ extern "C" int so_msda_backward(const float* value, const int64_t* spatial_shape
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   long long threads = (long long)B * Nq * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
+  ProfScope prof(5, st);
   SO_DISPATCH_DH(Dh,
                  (msda_backward_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, grad_out, grad_value, grad_loc, grad_weights, B, Nv, Hd, Nq, L, P)),
                  (msda_backward_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, loc, weights, grad_out, grad_value, grad_loc, grad_weights, B, Nv, Hd, Nq, L, P)));
@@ -423,6 +425,7 @@ extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spat
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   long long threads = (long long)Q * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
+  ProfScope prof(2, st);
   SO_DISPATCH_DH(Dh,
                  (tpv_cross_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)),
                  (tpv_cross_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)));
@@ -441,6 +444,7 @@ extern "C" int so_tpv_self_attn_forward(const float* value, const int64_t* spati
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   long long threads = (long long)Q * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
+  ProfScope prof(3, st);
   SO_DISPATCH_DH(Dh, (tpv_self_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)),
                  (tpv_self_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)));
   note_launch(1);

@@ -349,6 +349,7 @@ extern "C" int so_render_infer(const float* vol_sdf, const float* vol_feat, cons
   if ((rc = check_launch())) return rc;
 
   unsigned grid = (unsigned)ceil_div64(rd->ray_count, 128);
+  ProfScope prof(0, st);
   long long* midx = reinterpret_cast<long long*>(max_idx);
   if (want_sem)
     render_infer_kernel<true, true><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);

@@ -48,7 +48,7 @@ def tpv_decode_ref(tpv_hw, tpv_zh, tpv_wz, sizes, w1, b1, w2, b2, h_chunk=16):
 
 def field_query_ref(vol, mapping, x, with_grad=True):
     """vol [Cf,H,W,Z]; x [N,3] metres -> (h [N,Cf], grad_sdf [N,3] or None).  bev_nerf.py:155-170."""
-    x = x.detach().clone().requires_grad_(with_grad)
+    x = x.detach().to(vol.dtype).clone().requires_grad_(with_grad)
     with torch.enable_grad():
         g = mapping.meter2grid(x, True) * 2 - 1
         samp = F.grid_sample(vol[None], g.reshape(1, -1, 1, 1, 3)[..., [2, 1, 0]], mode='bilinear',

@@ -146,6 +146,30 @@ __device__ __forceinline__ void gather_sdf(const VolumeDev& v, const Taps& t, fl
   dgd = fmaf(t.fh, dz1 - dz0, dz0);
 }
 
+// interior fast path: all 8 corners inside the volume (true for every sample strictly inside the AABB)
+__device__ __forceinline__ void gather_sdf_interior(const VolumeDev& v, int h0, int w0, int z0, float fh, float fw,
+                                                    float fz, float& s, float& dgh, float& dgw, float& dgd) {
+  const int zp = v.zpitch;
+  const float* p00 = v.sdf + ((h0 * v.W + w0) * zp + z0);
+  const float* p01 = p00 + zp;
+  const float* p10 = p00 + v.W * zp;
+  const float* p11 = p10 + zp;
+  float a000 = __ldg(p00), a001 = __ldg(p00 + 1);
+  float a010 = __ldg(p01), a011 = __ldg(p01 + 1);
+  float a100 = __ldg(p10), a101 = __ldg(p10 + 1);
+  float a110 = __ldg(p11), a111 = __ldg(p11 + 1);
+  float dz00 = a001 - a000, dz01 = a011 - a010, dz10 = a101 - a100, dz11 = a111 - a110;
+  float c00 = fmaf(fz, dz00, a000), c01 = fmaf(fz, dz01, a010);
+  float c10 = fmaf(fz, dz10, a100), c11 = fmaf(fz, dz11, a110);
+  float dw0 = c01 - c00, dw1 = c11 - c10;
+  float c0 = fmaf(fw, dw0, c00), c1 = fmaf(fw, dw1, c10);
+  float dz0 = fmaf(fw, dz01 - dz00, dz00), dz1 = fmaf(fw, dz11 - dz10, dz10);
+  dgh = c1 - c0;
+  s = fmaf(fh, dgh, c0);
+  dgw = fmaf(fh, dw1 - dw0, dw0);
+  dgd = fmaf(fh, dz1 - dz0, dz0);
+}
+
 // trilinear gather of `n` consecutive feature channels starting at `c0` (channel-last volume)
 template <int N>
 __device__ __forceinline__ void gather_feat(const VolumeDev& v, const Taps& t, int c0, float out[N]) {
@@ -163,21 +187,35 @@ __device__ __forceinline__ void gather_feat(const VolumeDev& v, const Taps& t, i
   }
 }
 
+// sigmoid via one ex2.approx + one rcp.approx (abs error ~1e-7): exp(-|x|) never overflows
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e = __expf(-fabsf(x));
+  float s = __fdividef(1.0f, 1.0f + e);
+  return x >= 0.f ? s : e * s;
+}
 __device__ __forceinline__ float sigmoidf_acc(float x) {
   float e = expf(-fabsf(x));
   float s = 1.0f / (1.0f + e);
   return x >= 0.f ? s : e * s;
 }
 
+// 1 - exp(-x) for x >= 0 with ~1e-6 relative accuracy: 5-term series below 1/8, ex2.approx above
+__device__ __forceinline__ float one_minus_exp_neg(float x) {
+  float ser = x * (1.0f - x * 0.5f * (1.0f - x * (1.0f / 3.0f) * (1.0f - x * 0.25f * (1.0f - x * 0.2f))));
+  float big = 1.0f - __expf(-x);
+  return x < 0.125f ? ser : big;
+}
+
 // NeuS alpha = clip((Phi(prev) - Phi(next) + 1e-5) / (Phi(prev) + 1e-5), 0, 1) with Phi = sigmoid(inv_s * .),
 // prev = sdf - half, next = sdf + half (half <= 0).  The difference of the two CDFs is evaluated without
 // cancellation:  Phi(a) - Phi(b) = Phi(a) * Phi(-b) * (1 - exp(-(a - b))),  a - b = -2 * half * inv_s >= 0,
-// which keeps fp32 within rounding of the fp64 evaluation of the reference formula.
+// which keeps fp32 within rounding of the fp64 evaluation of the reference formula (the reference's own fp32
+// evaluation loses ~3 digits to cancellation here).
 __device__ __forceinline__ float neus_alpha(float sdf, float half, float inv_s) {
-  float a = (sdf - half) * inv_s, b = (sdf + half) * inv_s;
-  float pa = sigmoidf_acc(a);
-  float diff = pa * sigmoidf_acc(-b) * (-expm1f(2.0f * half * inv_s));
-  return fminf(fmaxf((diff + 1e-5f) / (pa + 1e-5f), 0.f), 1.f);
+  float hs = half * inv_s, ss = sdf * inv_s;
+  float pa = sigmoid_fast(ss - hs);
+  float diff = pa * sigmoid_fast(-(ss + hs)) * one_minus_exp_neg(-2.0f * hs);
+  return __saturatef(__fdividef(diff + 1e-5f, pa + 1e-5f));
 }
 
 constexpr float kC0 = 0.28209479177387814f;  // sh_render.py:4
@@ -190,7 +228,8 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
                                                            float* __restrict__ acc_out, float* __restrict__ normal_vis,
                                                            float* __restrict__ rgb_out, float* __restrict__ sem_out) {
   long long lid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (lid >= R.ray_count) return;
+  const bool valid = lid < R.ray_count;            // lanes past the end stay alive for the warp votes below
+  if (!valid) lid = R.ray_count - 1;
   long long gid = R.ray_begin + lid;
   float o[3], d[3], nrm, tn, tf;
   make_ray(R, gid, o, d, nrm);
@@ -198,7 +237,18 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
 
   const int S = P.S;
   const float step = 1.0f / (float)S;
-  const float eps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (neus_head.py:431)
+  const bool pow2 = (S & (S - 1)) == 0;            // then i * (1/S) is exact and equals torch.linspace bit for bit
+  const float eps = 1.1920928955078125e-07f;       // torch.finfo(float32).eps (neus_head.py:431)
+  const float eps_len = eps * nrm;                 // delta / nrm < eps  <=>  delta < eps * nrm
+  // metre -> grid is affine per axis when the mapping has no outer ring (every shipped config):
+  // g(t) = g0 + gd * t along the ray, one FMA per axis per sample
+  const bool affine = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f;
+  const float kh0 = V.ax[0].k0, kw0 = V.ax[1].k0, kd0 = V.ax[2].k0;
+  const float gh0 = fmaf(o[1] - V.ax[0].start, kh0, V.ax[0].offset), gdh = d[1] * kh0;
+  const float gw0 = fmaf(o[0] - V.ax[1].start, kw0, V.ax[1].offset), gdw = d[0] * kw0;
+  const float gd0 = fmaf(o[2] - V.ax[2].start, kd0, V.ax[2].offset), gdd = d[2] * kd0;
+  const int Hm1 = V.H - 1, Wm1 = V.W - 1, Zm1 = V.Z - 1;
+
   float T = 1.0f, acc = 0.f, dsum = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
   float best = -INFINITY, best_mid = 0.f;
   int best_i = 0;
@@ -211,17 +261,31 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
   float e0 = edge_t(bin_edge01(0, S, step), tn, tf);
 #pragma unroll 2
   for (int s = 0; s < S; ++s) {
-    float e1 = edge_t(bin_edge01(s + 1, S, step), tn, tf);
+    float b1 = pow2 ? (float)(s + 1) * step : bin_edge01(s + 1, S, step);
+    float e1 = edge_t(b1, tn, tf);
     float mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
     float delta = __fsub_rn(e1, e0);
     float tq = P.anchor_mid ? mid : e0;
     e0 = e1;
-    float x = fmaf(d[0], tq, o[0]), y = fmaf(d[1], tq, o[1]), z = fmaf(d[2], tq, o[2]);
-    float kh, kw, kd;
-    float gh = axis_m2g(V.ax[0], y, kh), gw = axis_m2g(V.ax[1], x, kw), gd = axis_m2g(V.ax[2], z, kd);
-    Taps t = make_taps(V, gh, gw, gd);
+    float gh, gw, gd, kh = kh0, kw = kw0, kd = kd0;
+    if (affine) {
+      gh = fmaf(gdh, tq, gh0); gw = fmaf(gdw, tq, gw0); gd = fmaf(gdd, tq, gd0);
+    } else {
+      float x = fmaf(d[0], tq, o[0]), y = fmaf(d[1], tq, o[1]), z = fmaf(d[2], tq, o[2]);
+      gh = axis_m2g(V.ax[0], y, kh); gw = axis_m2g(V.ax[1], x, kw); gd = axis_m2g(V.ax[2], z, kd);
+    }
     float sdf, dgh, dgw, dgd;
-    gather_sdf(V, t, sdf, dgh, dgw, dgd);
+    float flh = floorf(gh), flw = floorf(gw), flz = floorf(gd);
+    int h0 = (int)flh, w0 = (int)flw, z0 = (int)flz;
+    bool interior = (unsigned)h0 < (unsigned)Hm1 && (unsigned)w0 < (unsigned)Wm1 && (unsigned)z0 < (unsigned)Zm1;
+    Taps t;
+    if (__all_sync(0xffffffffu, interior)) {
+      gather_sdf_interior(V, h0, w0, z0, gh - flh, gw - flw, gd - flz, sdf, dgh, dgw, dgd);
+      if (HAS_RGB) t = make_taps(V, gh, gw, gd);
+    } else {
+      t = make_taps(V, gh, gw, gd);
+      gather_sdf(V, t, sdf, dgh, dgw, dgd);
+    }
     float gx = dgw * kw, gy = dgh * kh, gz = dgd * kd;  // d sdf / d metre (x, y, z)
     // NeuS alpha (upstream SDFField.get_alpha)
     float tc = d[0] * gx + d[1] * gy + d[2] * gz;
@@ -231,12 +295,11 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     T *= (1.0f - alpha + 1e-7f);
     acc += w;
     dsum = fmaf(w, mid, dsum);
-    float gn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);  // F.normalize eps
-    float wn = w / gn;
+    float wn = w * rsqrtf(fmaxf(gx * gx + gy * gy + gz * gz, 1e-24f));  // F.normalize(eps=1e-12)
     n0 = fmaf(wn, gx, n0); n1 = fmaf(wn, gy, n1); n2 = fmaf(wn, gz, n2);
-    // max-depth candidate (neus_head.py:430-438): first maximum of w / clamp(delta', eps), w := 0 where delta' < eps
-    float dl = delta / nrm;
-    float cand = (dl < eps ? 0.f : w) / fmaxf(dl, eps);
+    // max-depth candidate (neus_head.py:430-438): first maximum of w / clamp(delta', eps) with w := 0 where delta' < eps;
+    // delta' = delta / |dir| and |dir| is constant along the ray, so the argmax is taken over w / delta
+    float cand = delta < eps_len ? 0.f : __fdividef(w, delta);
     if (cand > best) { best = cand; best_i = s; best_mid = mid; }
     if (HAS_RGB) {
       float f[3];
@@ -257,6 +320,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
       for (int c = 0; c < n_sem; ++c) sem[c] = fmaf(sc, lg[c], sem[c]);
     }
   }
+  if (!valid) return;
 
   long long chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
   float lo = __ldg(ws + 2 * chunk), hi = __ldg(ws + 2 * chunk + 1);

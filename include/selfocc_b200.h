@@ -133,6 +133,35 @@ int so_render_infer(const float* vol_sdf, const float* vol_feat, const so_volume
                     float* depth, float* max_depth, int64_t* max_idx, float* acc,
                     float* normal_vis, float* rgb, float* sem, float* workspace, void* stream);
 
+/* B6-B10, B13  training-form render (NeuSHead.forward, neus_head.py:513-587): same sampling / field / alpha /
+ * compositing as so_render_infer but it EMITS the per-sample tensors the losses consume (:667-682) and has a
+ * backward.  `jitter` [total rays, S+1] uniforms in [0,1) for the stratified sampler (`perturb=True`), NULL =
+ * no jitter.  Per-ray outputs [n]: depth, acc, fars (far / |dir|), max_depth, rgb [n,3], sem [n,n_feat-3];
+ * per-sample outputs [n,S]: weights, ts = mid / |dir|, deltas = (end-start) / |dir|, sample_sdf; eik_grad [n,S,3]
+ * = d sdf / d metre at the samples.  Any output may be NULL.  S <= 256. */
+int so_render_train_forward(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                            const float* cam_mats, const float* pix, const so_ray_desc* rays_host,
+                            const so_render_params* params_host, const float* jitter, const float* bkgd_rand,
+                            float* depth, float* acc, float* fars, float* rgb, float* sem, float* max_depth,
+                            float* weights, float* ts, float* deltas, float* eik_grad, float* sample_sdf,
+                            float* workspace, void* stream);
+
+/* Backward of so_render_train_forward w.r.t. the decoded volume and inv_s.  Incoming gradients (NULL = zero):
+ * g_depth, g_acc [n], g_rgb [n,3], g_sem [n,n_feat-3], g_weights, g_sdf [n,S], g_eik [n,S,3].  Results are
+ * ACCUMULATED (atomically) into g_vol_sdf [H,W,zpitch], g_vol_feat [H,W,Z,feat_pitch] (needed iff g_rgb/g_sem)
+ * and the scalar g_inv_s; the caller zero-fills them.  Recomputes the forward (nothing is saved). */
+int so_render_train_backward(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
+                             const float* cam_mats, const float* pix, const so_ray_desc* rays_host,
+                             const so_render_params* params_host, const float* jitter, const float* bkgd_rand,
+                             const float* g_depth, const float* g_acc, const float* g_rgb, const float* g_sem,
+                             const float* g_weights, const float* g_eik, const float* g_sdf,
+                             float* g_vol_sdf, float* g_vol_feat, float* g_inv_s, float* workspace, void* stream);
+
+/* Backward of so_field_query: g_sdf [n], g_grad [n,3], g_feat [n,n_feat] (NULL = zero) accumulated into
+ * g_vol_sdf / g_vol_feat (caller zero-fills). */
+int so_field_query_backward(const so_volume_desc* vol_host, const float* points, int64_t n, const float* g_sdf,
+                            const float* g_grad, const float* g_feat, float* g_vol_sdf, float* g_vol_feat, void* stream);
+
 /* B12  field query at arbitrary points.  Replaces field.forward_sdfnetwork / forward_geonetwork
  * as used by NeuSHead.get_uniform_sdf (neus_head.py:265-293).  points [n,3] metres ->
  * sdf [n], grad [n,3] (NULL ok), feat [n, n_feat] raw decoded channels 1.. (NULL ok). */

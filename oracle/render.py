@@ -60,6 +60,44 @@ def field_query_ref(vol, mapping, x, with_grad=True):
     return h.detach(), grad
 
 
+def field_query_manual(vol, mapping, x):
+    """Same function as ``field_query_ref`` written as explicit 8-corner gathers so that BOTH outputs (values and
+    the analytic position-gradient) are differentiable w.r.t. ``vol`` -- PyTorch has no double backward for
+    ``grid_sampler_3d`` (the fork vendors ``cuda_gridsample_grad2`` for that, docs/installation.md:30).  Used by the
+    training-parity tests; checked against ``field_query_ref`` in tests/test_oracle_selfcheck.py."""
+    Cf, H, W, Z = vol.shape
+    x = x.to(vol.dtype)
+    g = mapping.meter2grid(x, False)
+    gh, gw, gd = g[:, 0], g[:, 1], g[:, 2]
+    h0, w0, z0 = gh.floor(), gw.floor(), gd.floor()
+    fh, fw, fz = gh - h0, gw - w0, gd - z0
+    h0, w0, z0 = h0.long(), w0.long(), z0.long()
+    val = vol.new_zeros(x.shape[0], Cf)
+    dgh = vol.new_zeros(x.shape[0])
+    dgw = vol.new_zeros(x.shape[0])
+    dgd = vol.new_zeros(x.shape[0])
+    for dh in (0, 1):
+        for dw in (0, 1):
+            for dz in (0, 1):
+                hh, ww, zz = h0 + dh, w0 + dw, z0 + dz
+                ok = (hh >= 0) & (hh < H) & (ww >= 0) & (ww < W) & (zz >= 0) & (zz < Z)
+                v = vol[:, hh.clamp(0, H - 1), ww.clamp(0, W - 1), zz.clamp(0, Z - 1)].t() * ok[:, None].to(vol.dtype)
+                wh = fh if dh else 1 - fh
+                w_w = fw if dw else 1 - fw
+                wz = fz if dz else 1 - fz
+                val = val + (wh * w_w * wz)[:, None] * v
+                dgh = dgh + (1.0 if dh else -1.0) * w_w * wz * v[:, 0]
+                dgw = dgw + wh * (1.0 if dw else -1.0) * wz * v[:, 0]
+                dgd = dgd + wh * w_w * (1.0 if dz else -1.0) * v[:, 0]
+    # chain rule through the per-axis piecewise-linear metre->grid map
+    xr = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        gg = mapping.meter2grid(xr, False)
+        slopes = torch.autograd.grad(gg.sum(), xr)[0]          # d(grid of own axis)/d(metre): (kw, kh, kd) in x,y,z order
+    grad = torch.stack([dgw * slopes[:, 0], dgh * slopes[:, 1], dgd * slopes[:, 2]], -1)
+    return val, grad
+
+
 def aabb_near_far(o, d, aabb, near_plane, training):
     """upstream AABBBoxCollider: slab test with 1/(d + 1e-6); near clamped to near_plane when
     training else 0; far >= near + 1e-6."""
@@ -91,7 +129,7 @@ def uniform_bins(nears, fars, S, jitter=None):
 
 def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=0.0, training=False,
                       jitter=None, cos_anneal=1.0, color_dims=0, sh_act='relu', bkgd='white',
-                      bkgd_rand=None, anchor='mid'):
+                      bkgd_rand=None, anchor='mid', differentiable=False):
     """One ``self.model(ray_bundle)`` call of the reference (neus_head.py:353/394/531) for a chunk
     of rays o,d [R,3] (d unit), dnorm [R,1].  Returns the dict the head consumes."""
     R = o.shape[0]
@@ -101,7 +139,10 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
     deltas = ends - starts
     tq = mids if anchor == 'mid' else starts
     x = o[:, None, :] + d[:, None, :] * tq[..., None]
-    h, grad = field_query_ref(vol, mapping, x.reshape(-1, 3))
+    if differentiable:
+        h, grad = field_query_manual(vol, mapping, x.reshape(-1, 3))
+    else:
+        h, grad = field_query_ref(vol, mapping, x.reshape(-1, 3))
     h = h.reshape(R, S, -1)
     grad = grad.reshape(R, S, 3)
     sdf = h[..., 0]

@@ -33,10 +33,6 @@ class RenderParams(C.Structure):
                 ('anchor_mid', C.c_int32), ('sh_act', C.c_int32), ('bkgd_mode', C.c_int32)]
 
 
-class TrainParams(C.Structure):
-    _fields_ = [('base', RenderParams), ('n_rays', C.c_int64)]
-
-
 _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
@@ -55,6 +51,11 @@ SIGNATURES = {
     'so_render_workspace_floats': (C.c_int64, [_L]),
     'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'so_render_train_forward': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
+                                          _P, _P] + [_P] * 11 + [_P, _P]),
+    'so_render_train_backward': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
+                                           _P, _P] + [_P] * 7 + [_P, _P, _P, _P, _P]),
+    'so_field_query_backward': (C.c_int, [C.POINTER(VolumeDesc), _P, _L, _P, _P, _P, _P, _P, _P]),
     'so_field_query': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _L, _P, _P, _P, _P]),
     'so_msda_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'so_msda_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

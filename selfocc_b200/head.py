@@ -219,9 +219,17 @@ class NeuSHead(nn.Module):
     def _sampler(self):
         return self.ray_sampler_eval if os.environ.get('eval', 'false') == 'true' else self.ray_sampler
 
+    def _inv_s(self):
+        """exp(10 * variance) as a host float, cached on the parameter's version so eval does not sync per frame."""
+        v = self.model.field.deviation_network.variance
+        key = (v._version, v.data_ptr())
+        if getattr(self, '_inv_s_key', None) != key:
+            self._inv_s_key, self._inv_s_val = key, float(self.model.field.deviation_network.get_variance())
+        return self._inv_s_val
+
     def _params(self, training):
         f = self.model.field
-        return ops.make_render_params(self.aabb, self.num_samples, float(f.deviation_network.get_variance()),
+        return ops.make_render_params(self.aabb, self.num_samples, self._inv_s(),
                                       near_plane=self.near_plane, training=training, cos_anneal=self.cos_anneal_ratio,
                                       anchor_mid=self.sample_anchor == 'mid', sh_act=f.sh_act, bkgd=self.render_bkgd)
 

@@ -226,3 +226,138 @@ def tpv_self_attn_forward(value, spatial_shapes, level_start_index, offsets, log
     _lib.check(lib.so_tpv_self_attn_forward(_p(value), _p(spatial_shapes), _p(level_start_index), _p(offsets), _p(logits),
                                             _p(ref), _p(out), Nv, Hd, Dh, Q, L, P, _stream()), 'so_tpv_self_attn_forward')
     return out
+
+
+# --------------------------------------------------------------------------------------- training form (B6-B10, B13)
+def _render_ws(lib, rays, dev):
+    total = rays.n_cam * rays.rays_per_cam
+    n_chunks = (total + rays.chunk_len - 1) // rays.chunk_len if rays.chunk_len > 0 else 1
+    return torch.empty(lib.so_render_workspace_floats(n_chunks), device=dev, dtype=torch.float32)
+
+
+class RenderTrainFunction(torch.autograd.Function):
+    """Differentiable (w.r.t. the decoded volume and inv_s) training-form render.
+    forward(vol_sdf, vol_feat_or_None, inv_s[1], cfg) -> (depth, acc, fars, max_depth, rgb, sem, weights, ts, deltas,
+    eik_grad, sample_sdf); entries not requested in cfg['want'] are returned as empty tensors."""
+
+    ORDER = ('depth', 'acc', 'fars', 'max_depth', 'rgb', 'sem', 'weights', 'ts', 'deltas', 'eik_grad', 'sample_sdf')
+
+    @staticmethod
+    def forward(ctx, vol_sdf, vol_feat, inv_s, cfg):
+        lib = _lib.load()
+        desc, cam_mats, rays, params = cfg['desc'], cfg['cam_mats'], cfg['rays'], cfg['params']
+        pix, jitter, bkgd = cfg.get('pix'), cfg.get('jitter'), cfg.get('bkgd_rand')
+        _chk(vol_sdf, name='vol_sdf'); _chk(vol_feat, name='vol_feat'); _chk(cam_mats, name='cam_mats')
+        _chk(pix, name='pix'); _chk(jitter, name='jitter'); _chk(bkgd, name='bkgd_rand')
+        n, S, dev = rays.ray_count, params.num_samples, vol_sdf.device
+        if jitter is not None:
+            assert jitter.shape == (rays.n_cam * rays.rays_per_cam, S + 1)
+        n_sem = max(desc.n_feat - 3, 0)
+        shapes = dict(depth=(n,), acc=(n,), fars=(n,), max_depth=(n,), rgb=(n, 3), sem=(n, n_sem), weights=(n, S), ts=(n, S),
+                      deltas=(n, S), eik_grad=(n, S, 3), sample_sdf=(n, S))
+        want = set(cfg['want'])
+        out = {k: (torch.empty(shapes[k], device=dev) if k in want else None) for k in RenderTrainFunction.ORDER}
+        ws = _render_ws(lib, rays, dev)
+        g = lambda k: _p(out[k])
+        _lib.check(lib.so_render_train_forward(
+            _p(vol_sdf), _p(vol_feat), C.byref(desc), _p(cam_mats), _p(pix), C.byref(rays), C.byref(params), _p(jitter), _p(bkgd),
+            g('depth'), g('acc'), g('fars'), g('rgb'), g('sem'), g('max_depth'), g('weights'), g('ts'), g('deltas'),
+            g('eik_grad'), g('sample_sdf'), _p(ws), _stream()), 'so_render_train_forward')
+        ctx.cfg = cfg
+        ctx.save_for_backward(vol_sdf, vol_feat if vol_feat is not None else vol_sdf.new_empty(0))
+        ctx.has_feat = vol_feat is not None
+        res = tuple(out[k] if out[k] is not None else vol_sdf.new_empty(0) for k in RenderTrainFunction.ORDER)
+        ctx.mark_non_differentiable(res[2], res[3], res[7], res[8])       # fars, max_depth, ts, deltas: geometry only
+        return res
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_depth, g_acc, g_fars, g_maxd, g_rgb, g_sem, g_weights, g_ts, g_deltas, g_eik, g_sdf):
+        lib = _lib.load()
+        cfg = ctx.cfg
+        vol_sdf, vol_feat = ctx.saved_tensors
+        vol_feat = vol_feat if ctx.has_feat else None
+        desc, rays, params = cfg['desc'], cfg['rays'], cfg['params']
+        want = set(cfg['want'])
+
+        def gr(name, t):
+            return t.contiguous() if (name in want and t is not None and t.numel()) else None
+        gd, ga, grgb, gsem = gr('depth', g_depth), gr('acc', g_acc), gr('rgb', g_rgb), gr('sem', g_sem)
+        gw, ge, gs = gr('weights', g_weights), gr('eik_grad', g_eik), gr('sample_sdf', g_sdf)
+        gvs = torch.zeros_like(vol_sdf)
+        gvf = torch.zeros_like(vol_feat) if vol_feat is not None else None
+        ginv = torch.zeros(1, device=vol_sdf.device)
+        ws = _render_ws(lib, rays, vol_sdf.device)
+        _lib.check(lib.so_render_train_backward(
+            _p(vol_sdf), _p(vol_feat), C.byref(desc), _p(cfg['cam_mats']), _p(cfg.get('pix')), C.byref(rays), C.byref(params),
+            _p(cfg.get('jitter')), _p(cfg.get('bkgd_rand')), _p(gd), _p(ga), _p(grgb), _p(gsem), _p(gw), _p(ge), _p(gs),
+            _p(gvs), _p(gvf), _p(ginv), _p(ws), _stream()), 'so_render_train_backward')
+        return gvs, gvf, ginv, None
+
+
+class FieldQueryFunction(torch.autograd.Function):
+    """Differentiable (w.r.t. the volume) point query: (vol_sdf, vol_feat, desc, points[n,3]) -> (sdf[n], grad[n,3], feat[n,nf])."""
+
+    @staticmethod
+    def forward(ctx, vol_sdf, vol_feat, desc, points, want_grad, want_feat):
+        s, g, f = field_query(vol_sdf, vol_feat, desc, points, want_grad=want_grad, want_feat=want_feat)
+        ctx.desc, ctx.has_feat = desc, vol_feat is not None
+        ctx.save_for_backward(points, vol_sdf, vol_feat if vol_feat is not None else vol_sdf.new_empty(0))
+        e = vol_sdf.new_empty(0)
+        return s, (g if g is not None else e), (f if f is not None else e)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_s, g_g, g_f):
+        lib = _lib.load()
+        points, vol_sdf, vol_feat = ctx.saved_tensors
+        gvs = torch.zeros_like(vol_sdf)
+        gvf = torch.zeros_like(vol_feat) if ctx.has_feat else None
+        opt = lambda t: t.contiguous() if (t is not None and t.numel()) else None
+        gf = opt(g_f) if ctx.has_feat else None
+        _lib.check(lib.so_field_query_backward(C.byref(ctx.desc), _p(points), points.shape[0], _p(opt(g_s)), _p(opt(g_g)),
+                                               _p(gf), _p(gvs), _p(gvf), _stream()), 'so_field_query_backward')
+        return gvs, gvf, None, None, None, None
+
+
+class TPVDecodeFunction(torch.autograd.Function):
+    """Decode with the fused sm_100a forward.  Backward (training only) recomputes the MLP slab by slab with
+    torch/cuBLAS -- bounded memory, never the reference's 750 MB intermediate; a native backward kernel is future work."""
+
+    @staticmethod
+    def forward(ctx, hw, zh, wz, w1, b1, w2, b2, desc):
+        ctx.desc = desc
+        ctx.save_for_backward(hw, zh, wz, w1, b1, w2, b2)
+        vs, vf = tpv_decode(hw.contiguous(), zh.contiguous(), wz.contiguous(), w1.contiguous(), b1.contiguous(),
+                            w2.contiguous(), b2.contiguous(), desc)
+        return vs, (vf if vf is not None else vs.new_empty(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_vs, g_vf):
+        import torch.nn.functional as F
+        hw, zh, wz, w1, b1, w2, b2 = ctx.saved_tensors
+        d = ctx.desc
+        H, W, Z, Cc = d.H, d.W, d.Z, hw.shape[-1]
+        g_out = g_vs[..., :Z, None]
+        if d.n_feat:
+            g_out = torch.cat([g_out, g_vf[..., :d.n_feat]], -1)
+        grads = [torch.zeros_like(t) for t in (hw, zh, wz, w1, b1, w2, b2)]
+        zh3, wz3 = zh.view(Z, H, Cc), wz.view(W, Z, Cc)
+        step = 8
+        for h0 in range(0, H, step):
+            h1 = min(H, h0 + step)
+            with torch.enable_grad():
+                a = hw.view(H, W, Cc)[h0:h1].detach().requires_grad_(True)
+                b = zh3[:, h0:h1].detach().requires_grad_(True)
+                c = wz3.detach().requires_grad_(True)
+                ws = [t.detach().requires_grad_(True) for t in (w1, b1, w2, b2)]
+                f = a[:, :, None, :] + b.permute(1, 0, 2)[:, None, :, :] + c[None]
+                out = F.linear(F.softplus(F.linear(F.softplus(f), ws[0], ws[1])), ws[2], ws[3])
+                gs = torch.autograd.grad(out, [a, b, c] + ws, g_out[h0:h1])
+            grads[0].view(H, W, Cc)[h0:h1] += gs[0]
+            grads[1].view(Z, H, Cc)[:, h0:h1] += gs[1]
+            grads[2].view(W, Z, Cc).add_(gs[2])
+            for i in range(4):
+                grads[3 + i] += gs[3 + i]
+        return (*grads, None)

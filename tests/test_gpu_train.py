@@ -1,0 +1,141 @@
+"""GPU parity of the training-form render (forward outputs + backward) and of NeuSHead.forward vs the oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from selfocc_b200 import synth, configs
+from selfocc_b200.mapping import GridMeterMapping
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    return torch.device('cuda:0')
+
+
+def _oracle_train(vol, mref, i2l, pix, aabb, inv_s, S, jitter, training, color_dims, bkgd_rand):
+    from oracle import rays as orays, render as orender
+    origin, direction = orays.img2lidar_rays(i2l[None], pix)
+    o, d, nrm = orays.flatten_rays(origin.double(), direction.double())
+    out = orender.neus_render_chunk(vol, mref, o, d, nrm, aabb, inv_s, S=S, near_plane=0.0, training=training, jitter=jitter,
+                                    color_dims=color_dims, bkgd='random' if bkgd_rand is not None else 'white',
+                                    bkgd_rand=bkgd_rand, differentiable=True)
+    out['ts'] = (out['starts'] + out['ends']) / 2 / nrm
+    out['deltas'] = (out['ends'] - out['starts']) / nrm
+    return out
+
+
+@pytest.mark.parametrize('n_feat,S,use_jitter', [(0, 64, False), (0, 48, True), (7, 40, True)])
+def test_render_train_forward_backward(n_feat, S, use_jitter):
+    dev = _dev()
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import rays as orays
+    from selfocc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    margs, aabb = synth.small_mapping(10, 6)
+    m, mref = GridMeterMapping(**margs), GridMeterMappingRef(**margs)
+    sdf = synth.analytic_sdf_volume(m, ground_z=-1.0, spheres=((3., 5., 0., 1.5),), boxes=(), noise=0.05, seed=1)
+    feat = torch.randn(n_feat, *sdf.shape, generator=g) if n_feat else None
+    _, i2l = synth.camera_rig(synth.NUSC_YAWS[:2], f=126.6, cx=80., cy=45., height=0.5, radius=0.2)
+    i2l = torch.tensor(i2l, dtype=torch.float32)
+    ny, nx = 5, 7
+    pix = orays.fixed_ray_grid([ny, nx], [90, 160])
+    n = 2 * ny * nx
+    jitter = torch.rand(n, S + 1, generator=g) if use_jitter else None
+    bk = torch.rand(n, 3, generator=g) if n_feat else None
+    inv_s0 = 12.0
+    # ---- oracle (fp64, differentiable through the manual field query)
+    vol64 = (sdf[None] if feat is None else torch.cat([sdf[None], feat], 0)).double().requires_grad_(True)
+    invs64 = torch.tensor(inv_s0, dtype=torch.float64, requires_grad=True)
+    ref = _oracle_train(vol64, mref, i2l, pix, aabb, invs64, S, jitter.double() if use_jitter else None, True,
+                        3 if n_feat else 0, bk.double() if bk is not None else None)
+    # ---- kernel
+    desc = m.volume_desc(n_feat)
+    vs = synth.pack_sdf_volume(sdf, desc.zpitch).to(dev).requires_grad_(True)
+    vf = synth.pack_feat_volume(feat, desc.feat_pitch).to(dev).requires_grad_(True) if n_feat else None
+    invs = torch.tensor([inv_s0], device=dev, requires_grad=True)
+    want = ['depth', 'acc', 'fars', 'max_depth', 'weights', 'ts', 'deltas', 'eik_grad', 'sample_sdf'] + (['rgb', 'sem'] if n_feat else [])
+    cfg = dict(desc=desc, cam_mats=i2l.to(dev), rays=ops.make_ray_desc(2, grid=(ny, nx, 160 / nx, 0., 90 / ny, 0.)),
+               params=ops.make_render_params(aabb, S, inv_s0, training=True, bkgd='random' if n_feat else 'white'),
+               jitter=jitter.to(dev) if use_jitter else None, bkgd_rand=bk.to(dev) if bk is not None else None, want=want)
+    res = dict(zip(ops.RenderTrainFunction.ORDER, ops.RenderTrainFunction.apply(vs, vf, invs, cfg)))
+    cmp = lambda a, b, atol, rtol=1e-4: torch.allclose(a.detach().cpu(), b.detach().float().reshape(a.shape), atol=atol, rtol=rtol)
+    assert cmp(res['weights'], ref['weights'], 2e-6)
+    assert cmp(res['ts'], ref['ts'], 1e-5, 1e-5) and cmp(res['deltas'], ref['deltas'], 1e-6, 1e-4)
+    assert cmp(res['eik_grad'], ref['eik_grad'], 2e-5) and cmp(res['sample_sdf'], ref['sdf'], 2e-5)
+    assert cmp(res['depth'], ref['depth'], 1e-5) and cmp(res['acc'], ref['accumulation'], 2e-5)
+    assert cmp(res['fars'], ref['fars'], 1e-5)
+    if n_feat:
+        assert cmp(res['rgb'], ref['rgb'], 5e-5) and cmp(res['sem'], ref['sem'], 5e-5)
+    # ---- backward with random cotangents on every differentiable output
+    keys = [('depth', 'depth'), ('acc', 'accumulation'), ('weights', 'weights'), ('eik_grad', 'eik_grad'), ('sample_sdf', 'sdf')]
+    if n_feat:
+        keys += [('rgb', 'rgb'), ('sem', 'sem')]
+    cot = {k: torch.randn(res[k].shape, generator=g) for k, _ in keys}
+    loss = sum((res[k] * cot[k].to(dev)).sum() for k, _ in keys)
+    loss.backward()
+    loss64 = sum((ref[rk].reshape(cot[k].shape) * cot[k].double()).sum() for k, rk in keys)
+    loss64.backward()
+    gv = vs.grad[..., :m.size_d].cpu()
+    gref = vol64.grad[0].float()
+    scale = gref.abs().max().item()
+    err = (gv - gref).abs().max().item()
+    print('train bwd: d/d(vol sdf) max abs err %.3e (max |g| %.3e); d/d(inv_s) %.6e vs %.6e' % (
+        err, scale, invs.grad.item(), invs64.grad.item()))
+    assert err < 2e-4 * max(scale, 1.0)
+    assert abs(invs.grad.item() - invs64.grad.item()) < 2e-4 * max(1.0, abs(invs64.grad.item()))
+    if n_feat:
+        gf = vf.grad[..., :n_feat].cpu().permute(3, 0, 1, 2)
+        assert torch.allclose(gf, vol64.grad[1:].float(), atol=2e-4 * max(1.0, vol64.grad[1:].abs().max().item()))
+
+
+def test_head_forward_training_outputs_and_grads():
+    """NeuSHead.forward (neus_head.py:473-713): output dict contract + gradients reach the TPV planes and the MLP."""
+    dev = _dev()
+    from selfocc_b200.registry import build_head
+    import selfocc_b200.segmentor  # noqa: F401
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender, rays as orays
+    torch.manual_seed(0)
+    margs, rng = synth.small_mapping(8, 4, rng=20.0, z0=-2.0, z1=4.0)
+    cfg = configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=6, num_layers=1, num_points_cross=(6, 6, 4),
+                                  num_points_self=4, num_samples=32, ray_number=(4, 6), ray_img_size=(90, 160), color_dims=7,
+                                  return_sem=True, render_bkgd='random')
+    head = build_head(cfg['head']).to(dev).train()
+    with torch.no_grad():
+        head.model.field.deviation_network.variance.fill_(0.25)
+    l2i, i2l = synth.camera_rig(f=126.6, cx=80., cy=45., height=0.5, radius=0.2)
+    metas = [dict(lidar2img=list(l2i), img2lidar=list(i2l), img_shape=(90, 160))]
+    H, W, Z = 17, 17, 5
+    planes = [(0.5 * torch.randn(1, n, 96, device=dev)).requires_grad_(True) for n in (H * W, Z * H, W * Z)]
+    n = 6 * 24
+    jitter = torch.rand(n, 33, device=dev)
+    bk = torch.rand(n, 3, device=dev)
+    out = head(representation=planes, metas=metas, jitter=jitter, bkgd_rand=bk)
+    for k in ('ms_depths', 'ms_colors', 'ms_accs', 'ms_fars', 'ms_rays', 'origin', 'direction', 'direction_norm', 'ray_indices',
+              'weights', 'ts', 'deltas', 'eik_grad', 'uniform_sdf', 'ms_max_depths', 'sem'):
+        assert k in out, k
+    assert out['ms_depths'][0].shape == (1, 6, 24) and out['ms_colors'][0].shape == (1, 6, 24, 3)
+    assert len(out['weights']) == 6 and out['weights'][0].shape == (24 * 32,)
+    assert torch.equal(out['ray_indices'][0], torch.arange(24, device=dev).repeat_interleave(32))
+    assert out['eik_grad'].shape == (n, 32, 3)
+    # oracle forward on the same planes / jitter
+    f = head.model.field
+    w1, b1, w2, b2 = (t.detach().cpu().double() for t in (f.density_net[1].weight, f.density_net[1].bias,
+                                                         f.density_net[3].weight, f.density_net[3].bias))
+    mref = GridMeterMappingRef(**margs)
+    vol = orender.tpv_decode_ref(*[p[0].detach().cpu().double() for p in planes], (H, W, Z), w1, b1, w2, b2)
+    origin, direction = orays.img2lidar_rays(torch.tensor(i2l, dtype=torch.float32)[None], orays.fixed_ray_grid([4, 6], [90, 160]))
+    o, d, nrm = orays.flatten_rays(origin.double(), direction.double())
+    ref = orender.neus_render_chunk(vol, mref, o, d, nrm, rng, float(f.deviation_network.get_variance()), S=32, training=True,
+                                    jitter=jitter.cpu().double(), color_dims=3, bkgd='random', bkgd_rand=bk.cpu().double())
+    assert torch.allclose(out['ms_depths'][0].detach().cpu().reshape(-1), ref['depth'].float(), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(torch.cat(out['weights']).detach().cpu(), ref['weights'].float().reshape(-1), atol=3e-6)
+    assert torch.allclose(out['ms_colors'][0].detach().cpu().reshape(-1, 3), ref['rgb'].float(), atol=5e-5)
+    loss = out['ms_depths'][0].mean() + torch.cat(out['weights']).pow(2).sum() + (out['eik_grad'].norm(dim=-1) - 1).pow(2).mean() \
+        + out['ms_colors'][0].mean() + out['sem'][0].pow(2).mean()
+    loss.backward()
+    for p in planes:
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+    assert f.density_net[1].weight.grad.abs().sum() > 0 and f.deviation_network.variance.grad is not None

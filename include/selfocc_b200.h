@@ -43,9 +43,9 @@ int64_t so_launch_count(void);
 /* Optional per-kernel device timing (used by bench.py for the roofline line).  When enabled, the entry
  * points bracket their dominant kernel with cudaEventRecord on the launch stream.  Tags:
  * 0 render_infer, 1 tpv_decode, 2 tpv_cross_attn, 3 tpv_self_attn, 4 msda_forward, 5 msda_backward,
- * 6 render_train_fwd, 7 render_train_bwd.  so_profile_elapsed_ms returns the SUM over the calls since
+ * 6 render_train_fwd, 7 render_train_bwd, 8 linear_3xtf32.  so_profile_elapsed_ms returns the SUM over the calls since
  * the last so_profile_reset (the caller must have synchronised the stream) and the call count. */
-#define SO_PROF_NUM_TAGS 8
+#define SO_PROF_NUM_TAGS 10
 int so_profile_enable(int on);
 int so_profile_reset(void);
 int so_profile_elapsed_ms(int tag, float* total_ms_host, int32_t* calls_host);
@@ -191,6 +191,16 @@ int so_msda_backward(const float* value, const int64_t* spatial_shapes, const in
                      float* grad_value, float* grad_loc, float* grad_weights,
                      int32_t B, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Nq, int32_t L, int32_t P,
                      void* stream);
+
+/* A6/A9  dense projection on the tcgen05 tensor cores with fp32-level accuracy ("3xTF32" operand splitting):
+ *     y[M,N] = act(x[M,K] * w[N,K]^T + bias[N]) (+ residual[M,N])
+ * Replaces the nn.Linear calls of the attention modules and the FFN (image_cross_attention.py:36,218-223,309-317,
+ * cross_view_hybrid_attention.py:79-86,118, tpvformer_encoder_layer.py:198-206).  w_hi / w_lo = so_split_tf32(w)
+ * (w_hi = w with the low 13 mantissa bits cleared, w_lo = w - w_hi), computed once per weight.  K % 96 == 0;
+ * x, w_hi, w_lo 16-byte aligned; relu: 0/1; bias / residual may be NULL. */
+int so_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream);
+int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                     float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 
 /* A4  projection of pillar reference points into the cameras.  Replaces point_sampling
  * (model/encoder/bevformer/utils.py:116-206, no post_rots / focal_ratios branch).

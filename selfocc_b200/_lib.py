@@ -59,6 +59,8 @@ SIGNATURES = {
     'so_field_query': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _L, _P, _P, _P, _P]),
     'so_msda_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'so_msda_backward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'so_split_tf32': (C.c_int, [_P, _P, _P, _L, _P]),
+    'so_linear_3xtf32': (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     'so_point_sampling': (C.c_int, [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     'so_tpv_cross_attn_forward': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'so_visible_index_lists': (C.c_int, [_P, _I, _I, _I, _P, _P, _P]),
@@ -107,7 +109,7 @@ def launch_count():
 
 
 PROF_TAGS = ('render_infer', 'tpv_decode', 'tpv_cross_attn', 'tpv_self_attn', 'msda_forward', 'msda_backward',
-             'render_train_fwd', 'render_train_bwd')
+             'render_train_fwd', 'render_train_bwd', 'linear_3xtf32', 'reserved')
 
 
 def profile_enable(on=True):

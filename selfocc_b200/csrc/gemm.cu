@@ -1,0 +1,333 @@
+// Dense projections of the lifting path on the 5th-gen tensor cores (value / offset /
+// weight / output Linear, FFN) with fp32-level accuracy:  Y = act(X W^T + b) [+ R]
+//
+//   X [M, K] fp32, W [N, K] fp32 (torch Linear layout, both K-major)  ->  Y [M, N] fp32
+//
+// Accuracy: the path feeds a 1e-4-relative depth bar, so plain TF32 (10-bit mantissa) is not acceptable.  Each
+// operand is split  v = hi + lo,  hi = v rounded to the nearest TF32 number (low 13 mantissa bits zero), lo = v - hi
+// (exact in fp32), and the product is accumulated as  hi*hi + lo*hi + hi*lo  in the fp32 TMEM accumulator
+// ("3xTF32", error ~2^-21).  W is split once on the host side (so_split_tf32); X is split in shared memory.
+//
+// Structure (one CTA = one 128 x BN output tile, 4 warps):
+//   TMA (cp.async.bulk.tensor.2d, 128B swizzle)  global -> smem   X tile [128 x 96] raw, W_hi / W_lo tiles [BN x 96]
+//   all threads: split X in place (hi) + second buffer (lo); fence.proxy.async
+//   one thread:  36 x tcgen05.mma.cta_group::1.kind::tf32  (3 products x 12 k-steps of 8), fp32 accumulator in TMEM
+//   tcgen05.commit -> mbarrier;  epilogue: tcgen05.ld 32x32b -> +bias, ReLU, +residual -> smem stage -> coalesced stores
+// K is consumed in chunks of 96 (3 swizzle atoms of 32 floats) that reuse the same buffers, so K = 192 (FFN) works too.
+// These GEMMs are HBM/L2-bound (K is tiny): M x (K + N) x 4 bytes per call.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace so {
+
+constexpr int kBM = 128;            // rows per CTA tile (UMMA M)
+constexpr int kAtomK = 32;          // fp32 elements per 128-byte swizzle atom
+constexpr int kChunkAtoms = 3;      // K chunk = 96
+constexpr int kAtomBytesA = kBM * 128;
+constexpr int kMaxBN = 128;
+constexpr int kGemmThreads = 128;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major fp32 matrix [rows, cols] (cols contiguous), box = [box_rows x 32 floats], 128-byte swizzle, zero OOB fill
+static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return SO_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kAtomK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SO_OK : SO_ERR_CUDA;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    if (++spins > (1u << 26)) __trap();   // a lost TMA / MMA completion must fail loudly, never hang the GPU
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart (cute SmemDescriptor, sm100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);        // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN (cute UMMA::InstrDescriptor)
+__host__ __device__ inline uint32_t make_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+// nearest TF32 number (low 13 mantissa bits zero), so the tensor core's own operand truncation is exact on it and the
+// remainder v - hi (exact in fp32) is at most half a TF32 ulp
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u & 0xffffe000u);
+}
+
+struct GemmSmem {
+  // offsets are relative to a 1024-byte aligned base
+  static constexpr int a_hi = 0;
+  static constexpr int a_lo = a_hi + kChunkAtoms * kAtomBytesA;
+  static constexpr int b_hi = a_lo + kChunkAtoms * kAtomBytesA;
+  static constexpr int b_lo = b_hi + kChunkAtoms * kMaxBN * 128;
+  static constexpr int bars = b_lo + kChunkAtoms * kMaxBN * 128;
+  static constexpr int total = bars + 64;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                     const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
+                     const float* __restrict__ residual, float* __restrict__ y, long long M, int N, int K, int BN, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + GemmSmem::bars);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kMaxBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc(BN);
+  const int n_chunks = K / (kChunkAtoms * kAtomK);
+  const uint32_t chunk_bytes = kChunkAtoms * (kAtomBytesA + 2 * BN * 128);
+
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const uint32_t parity = ch & 1;
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, chunk_bytes);
+      for (int a = 0; a < kChunkAtoms; ++a) {
+        int k0 = (ch * kChunkAtoms + a) * kAtomK;
+        tma_load_2d(sm + GemmSmem::a_hi + a * kAtomBytesA, &map_x, k0, (int)m0, bar_load);
+        tma_load_2d(sm + GemmSmem::b_hi + a * BN * 128, &map_whi, k0, n0, bar_load);
+        tma_load_2d(sm + GemmSmem::b_lo + a * BN * 128, &map_wlo, k0, n0, bar_load);
+      }
+    }
+    mbar_wait(bar_load, parity);
+    // split X: hi = nearest TF32 number, lo = exact remainder.  Element-wise, so the swizzle is irrelevant.
+    {
+      float4* hi = reinterpret_cast<float4*>(sm + GemmSmem::a_hi);
+      float4* lo = reinterpret_cast<float4*>(sm + GemmSmem::a_lo);
+      constexpr int n4 = kChunkAtoms * kAtomBytesA / 16;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += kGemmThreads) {
+        float4 v = hi[i], h, l;
+        h.x = tf32_rn(v.x); l.x = v.x - h.x;
+        h.y = tf32_rn(v.y); l.y = v.y - h.y;
+        h.z = tf32_rn(v.z); l.z = v.z - h.z;
+        h.w = tf32_rn(v.w); l.w = v.w - h.w;
+        hi[i] = h;
+        lo[i] = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ahi = smem_u32(sm + GemmSmem::a_hi), alo = smem_u32(sm + GemmSmem::a_lo);
+      const uint32_t bhi = smem_u32(sm + GemmSmem::b_hi), blo = smem_u32(sm + GemmSmem::b_lo);
+      uint32_t accum = ch > 0 ? 1u : 0u;
+#pragma unroll
+      for (int prod = 0; prod < 3; ++prod) {
+        const uint32_t abase = prod == 1 ? alo : ahi;
+        const uint32_t bbase = prod == 2 ? blo : bhi;
+        for (int a = 0; a < kChunkAtoms; ++a) {
+#pragma unroll
+          for (int k = 0; k < kAtomK / 8; ++k) {     // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+            uint64_t da = make_desc(abase + a * kAtomBytesA + k * 32);
+            uint64_t db = make_desc(bbase + a * BN * 128 + k * 32);
+            umma_tf32(tmem_base, da, db, idesc, accum);
+            accum = 1u;
+          }
+        }
+      }
+      umma_commit(bar_mma);     // implies tcgen05.fence::before_thread_sync
+    }
+    mbar_wait(bar_mma, parity);  // the MMAs have consumed this chunk's smem; accumulators (after the last chunk) are final
+    tc_fence_after();
+  }
+
+  // ---- epilogue: TMEM -> registers -> (+bias, relu, +residual) -> smem stage -> coalesced global stores
+  float* stage = reinterpret_cast<float*>(sm);                 // reuses the A buffers: 128 x 132 floats <= 96 KB
+  const int ldst = ((BN + 31) / 32) * 32 + 4;                  // tcgen05.ld works in 32-column groups
+  const int row = warp * 32 + lane;                            // TMEM lane == tile row
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      *reinterpret_cast<float4*>(stage + row * ldst + c0 + j) = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kMaxBN);
+  const int vec_per_row = BN / 4;
+  for (int i = tid; i < kBM * vec_per_row; i += kGemmThreads) {
+    int r_ = i / vec_per_row, c4 = (i - r_ * vec_per_row) * 4;
+    long long gr = m0 + r_;
+    int gc = n0 + c4;
+    if (gr >= M || gc >= N) continue;
+    float4 v = *reinterpret_cast<const float4*>(stage + r_ * ldst + c4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (gc + j < N) {
+        float t = o[j] + (bias ? __ldg(bias + gc + j) : 0.f);
+        if (relu) t = fmaxf(t, 0.f);
+        o[j] = t;
+      }
+    }
+    float* dst = y + gr * N + gc;
+    if (gc + 3 < N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      if (residual) {
+        float4 rr = __ldg(reinterpret_cast<const float4*>(residual + gr * N + gc));
+        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+      }
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (int j = 0; j < 4 && gc + j < N; ++j) dst[j] = o[j] + (residual ? __ldg(residual + gr * N + gc + j) : 0.f);
+    }
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = w[i];
+  float h = tf32_rn(v);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+}  // namespace so
+
+using namespace so;
+
+extern "C" int so_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
+  if (!w || !hi || !lo || n < 0) return SO_ERR_INVALID_ARG;
+  if (n == 0) return SO_OK;
+  split_tf32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                                float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
+  if (!x || !w_hi || !w_lo || !y || M < 0 || N < 1 || K < 1) return SO_ERR_INVALID_ARG;
+  if (K % (kChunkAtoms * kAtomK) != 0) return SO_ERR_UNSUPPORTED;                 // K multiple of 96
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15)
+    return SO_ERR_INVALID_ARG;                                                    // TMA needs 16-byte aligned bases
+  if (M == 0) return SO_OK;
+  if (M > 0x7fffffffLL) return SO_ERR_UNSUPPORTED;
+  int BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
+  CUtensorMap mx, mhi, mlo;
+  int rc;
+  if ((rc = make_tmap(&mx, x, M, K, kBM))) return rc;
+  if ((rc = make_tmap(&mhi, w_hi, N, K, BN))) return rc;
+  if ((rc = make_tmap(&mlo, w_lo, N, K, BN))) return rc;
+  static bool attr_set = false;
+  const int smem = GemmSmem::total + 1024;
+  if (!attr_set) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)))) return rc;
+    attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)ceil_div64(M, kBM), (unsigned)ceil_div64(N, BN));
+  ProfScope prof(8, st);
+  linear_3xtf32_kernel<<<grid, kGemmThreads, smem, st>>>(mx, mhi, mlo, bias, residual, y, (long long)M, N, K, BN, relu);
+  note_launch(1);
+  return check_launch();
+}

@@ -137,6 +137,25 @@ class _DeformBase(nn.Module):
         nn.init.constant_(self.value_proj.bias, 0.)
 
 
+def fast_linear(lin, x, relu=False, residual=None):
+    """nn.Linear forward for the inference path: the tcgen05 split-precision GEMM (``so_linear_3xtf32``) when the shape
+    allows it (K % 96 == 0), cuBLAS otherwise.  Split weights are cached per parameter version."""
+    w = lin.weight
+    if x.is_cuda and x.dtype == torch.float32 and ops.linear_supported(w.shape[1]):
+        ver = (w._version, w.data_ptr())
+        ent = getattr(lin, '_so_split', None)       # kept on the module itself: no aliasing between models
+        if ent is None or ent[0] != ver:
+            with torch.no_grad():
+                ent = (ver,) + ops.split_tf32(w.detach().contiguous())
+            lin._so_split = ent
+        return ops.linear_3xtf32(x.contiguous(), ent[1], ent[2], lin.bias.detach() if lin.bias is not None else None,
+                                 relu=relu, residual=None if residual is None else residual.contiguous())
+    out = F.linear(x, w, lin.bias)
+    if relu:
+        out = F.relu(out)
+    return out if residual is None else out + residual
+
+
 def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -172,26 +191,32 @@ class CrossViewHybridAttention(_DeformBase):
             query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
         bs, num_query, _ = query.shape
         num_value = value.shape[1]
+        Hd, L, P = self.num_heads, self.num_levels, self.num_points
+        if reference_points.shape[-1] != 2:
+            raise ValueError('Last dim of reference_points must be 2, but get %d instead.' % reference_points.shape[-1])
+        fused = bs == 1 and key_padding_mask is None and not _needs_grad(value, query, self.value_proj.weight)
+        if fused:   # inference: tensor-core projections + one fused sampling kernel, dropout is the identity
+            v = fast_linear(self.value_proj, value[0]).view(num_value, Hd, -1)
+            offsets = fast_linear(self.sampling_offsets, query[0]).view(num_query, Hd, L, P, 2)
+            logits = fast_linear(self.attention_weights, query[0]).view(num_query, Hd, L, P)
+            ref = reference_points[0] if reference_points.dim() == 5 else reference_points
+            out = ops.tpv_self_attn_forward(v, spatial_shapes, level_start_index, offsets, logits, ref.contiguous())
+            idt = identity[0] if self.batch_first else identity[:, 0]
+            if self.training:
+                out = self.dropout(fast_linear(self.output_proj, out)) + idt
+            else:
+                out = fast_linear(self.output_proj, out, residual=idt)
+            return out[None] if self.batch_first else out[:, None]
         value = self.value_proj(value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
-        Hd, L, P = self.num_heads, self.num_levels, self.num_points
         value = value.view(bs, num_value, Hd, -1)
         offsets = self.sampling_offsets(query).view(bs, num_query, Hd, L, P, 2)
         logits = self.attention_weights(query).view(bs, num_query, Hd, L * P)
-        if reference_points.shape[-1] != 2:
-            raise ValueError('Last dim of reference_points must be 2, but get %d instead.' % reference_points.shape[-1])
-        if bs == 1 and not _needs_grad(value, offsets, logits):
-            ref = reference_points[0] if reference_points.dim() == 5 else reference_points
-            out = ops.tpv_self_attn_forward(value[0].contiguous(), spatial_shapes, level_start_index,
-                                            offsets[0].contiguous(), logits.view(num_query, Hd, L, P).contiguous(),
-                                            ref.contiguous())[None]
-        else:
-            aw = logits.softmax(-1).view(bs, num_query, Hd, L, P)
-            normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).to(offsets.dtype)
-            loc = reference_points[:, :, None, :, :, :] + offsets / normalizer[None, None, None, :, None, :]
-            out = ops.MultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index, loc, aw,
-                                                             self.im2col_step)
+        aw = logits.softmax(-1).view(bs, num_query, Hd, L, P)
+        normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).to(offsets.dtype)
+        loc = reference_points[:, :, None, :, :, :] + offsets / normalizer[None, None, None, :, None, :]
+        out = ops.MultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index, loc, aw, self.im2col_step)
         out = self.output_proj(out)
         if not self.batch_first:
             out = out.permute(1, 0, 2)
@@ -275,16 +300,17 @@ class BEVCrossAttention(nn.Module):
         assert reference_points_cams.size(3) == D
         if bs == 1 and not _needs_grad(query, value, da.value_proj.weight):
             n_cam, nv = value.shape[0], value.shape[1]
-            v = da.value_proj(value[:, :, 0]).view(n_cam, nv, Hd, -1)
-            offsets = da.sampling_offsets(query[0]).view(num_query, Hd, L, D, 2)
-            logits = da.attention_weights(query[0]).view(num_query, Hd, L, D)
+            v = fast_linear(da.value_proj, value[:, :, 0]).view(n_cam, nv, Hd, -1)
+            offsets = fast_linear(da.sampling_offsets, query[0]).view(num_query, Hd, L, D, 2)
+            logits = fast_linear(da.attention_weights, query[0]).view(num_query, Hd, L, D)
             if bev_vis is None:
                 bev_vis = (bev_masks[:, 0].sum(-1) > 0).to(torch.uint8)
-            slots = ops.tpv_cross_attn_forward(v.contiguous(), spatial_shapes, level_start_index, offsets.contiguous(),
-                                               logits.contiguous(), reference_points_cams[:, 0].contiguous(),
-                                               bev_vis.contiguous())[None]
-        else:
-            slots = self._rebatch_forward(query, value, spatial_shapes, reference_points_cams, bev_masks, level_start_index)
+            slots = ops.tpv_cross_attn_forward(v, spatial_shapes, level_start_index, offsets, logits,
+                                               reference_points_cams[:, 0].contiguous(), bev_vis.contiguous())
+            if self.training:
+                return self.dropout(fast_linear(self.output_proj, slots))[None] + residual
+            return fast_linear(self.output_proj, slots, residual=residual[0])[None]
+        slots = self._rebatch_forward(query, value, spatial_shapes, reference_points_cams, bev_masks, level_start_index)
         slots = self.output_proj(slots)
         return self.dropout(slots) + residual
 
@@ -354,6 +380,10 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
 
     def forward(self, x, identity=None):
+        if not self.training and not _needs_grad(x, self.layers[0][0].weight):
+            h = fast_linear(self.layers[0][0], x, relu=True)
+            idt = (x if identity is None else identity) if self.add_identity else None
+            return fast_linear(self.layers[1], h, residual=idt)
         out = self.layers(x)
         if not self.add_identity:
             return out
@@ -539,9 +569,23 @@ class TPVFormerEncoder(nn.Module):
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         return torch.cat(feats, 2).permute(0, 2, 1, 3).contiguous(), spatial_shapes, level_start_index
 
+    def _tpv_pos(self):
+        """Positional embeddings depend on the weights only: recomputed per call under autograd (training), cached per
+        parameter version otherwise (tpvformer_encoder.py:254 recomputes them every frame)."""
+        pe = self.positional_encoding
+        ws = [pe.position_layer_hw.weight, pe.position_layer_zh.weight, pe.position_layer_wz.weight,
+              pe.position_layer_hw.bias, pe.position_layer_zh.bias, pe.position_layer_wz.bias]
+        if torch.is_grad_enabled() and any(w.requires_grad for w in ws):
+            return pe()
+        key = tuple((w._version, w.data_ptr()) for w in ws)
+        if getattr(self, '_pos_key', None) != key:
+            with torch.no_grad():
+                self._pos_key, self._pos_val = key, pe()
+        return self._pos_val
+
     def forward(self, representation, ms_img_feats=None, metas=None, **kwargs):
         bs = ms_img_feats[0].shape[0]
-        tpv_pos = [p.unsqueeze(0).repeat(bs, 1, 1) for p in self.positional_encoding()]
+        tpv_pos = [p.unsqueeze(0).repeat(bs, 1, 1) if bs > 1 else p.unsqueeze(0) for p in self._tpv_pos()]
         feat_flatten, spatial_shapes, level_start_index = self.flatten_features(ms_img_feats)
         tpv_embed = self.forward_layers(representation, feat_flatten, feat_flatten, tpv_pos=tpv_pos,
                                         spatial_shapes=spatial_shapes, level_start_index=level_start_index, img_metas=metas)

@@ -361,3 +361,32 @@ class TPVDecodeFunction(torch.autograd.Function):
             for i in range(4):
                 grads[3 + i] += gs[3 + i]
         return (*grads, None)
+
+
+# --------------------------------------------------------------------------------------- A6/A9 tensor-core projections
+def split_tf32(w):
+    """w fp32 -> (w_hi, w_lo) for the 3xTF32 GEMM (once per weight)."""
+    lib = _lib.load()
+    _chk(w, name='weight')
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(lib.so_split_tf32(_p(w), _p(hi), _p(lo), w.numel(), _stream()), 'so_split_tf32')
+    return hi, lo
+
+
+def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None):
+    """y = act(x @ w^T + bias) (+ residual) on tcgen05 tensor cores with fp32-level accuracy.  x [..., K] contiguous."""
+    lib = _lib.load()
+    _chk(x, name='x'); _chk(w_hi, name='w_hi'); _chk(w_lo, name='w_lo'); _chk(bias, name='bias'); _chk(residual, name='residual')
+    N, K = w_hi.shape
+    assert x.shape[-1] == K
+    M = x.numel() // K
+    y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    if residual is not None:
+        assert residual.shape == y.shape
+    _lib.check(lib.so_linear_3xtf32(_p(x), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(y), M, N, K, int(bool(relu)), _stream()),
+               'so_linear_3xtf32')
+    return y
+
+
+def linear_supported(K):
+    return K % 96 == 0

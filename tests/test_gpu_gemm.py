@@ -1,0 +1,36 @@
+"""GPU parity of the tcgen05 3xTF32 projection GEMM vs an fp64 reference (and vs cuBLAS fp32 for context)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('M,N,K,relu,res', [(1000, 96, 96, False, False), (4099, 432, 96, False, False), (257, 192, 96, True, False),
+                                            (3000, 96, 192, False, True), (70000, 1152, 96, False, False), (128, 216, 96, False, True),
+                                            (85, 72, 96, False, True), (459, 144, 96, True, False), (50, 24, 192, False, False)])
+def test_linear_3xtf32_matches_fp64(M, N, K, relu, res):
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    from selfocc_b200 import ops
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.2).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    r = torch.randn(M, N, generator=g).to(dev) if res else None
+    hi, lo = ops.split_tf32(w)
+    assert torch.equal(hi + lo, w)
+    y = ops.linear_3xtf32(x, hi, lo, b, relu=relu, residual=r)
+    ref = x.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.clamp(min=0)
+    if res:
+        ref = ref + r.double()
+    err = (y.double() - ref).abs().max().item()
+    cublas = torch.nn.functional.linear(x, w, b)
+    cublas = cublas.clamp(min=0) if relu else cublas
+    cublas = cublas + r if res else cublas
+    err_cublas = (cublas.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print('3xTF32 GEMM M=%d N=%d K=%d: max abs err %.3e (cuBLAS fp32 %.3e), |y|max %.2f' % (M, N, K, err, err_cublas, scale))
+    assert err < 2e-5 * max(scale, 1.0)

@@ -176,7 +176,7 @@ __device__ __forceinline__ void softmax_stats(const float* __restrict__ lg, int 
 #pragma unroll
   for (int s = LPI / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
   float sum = 0.f;
-  for (int i = lc; i < n; i += LPI) sum += expf(__ldg(lg + i) - m);
+  for (int i = lc; i < n; i += LPI) sum += __expf(__ldg(lg + i) - m);
 #pragma unroll
   for (int s = LPI / 2; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
   mx = m;
@@ -184,18 +184,22 @@ __device__ __forceinline__ void softmax_stats(const float* __restrict__ lg, int 
 }
 
 // ---- A5+A6+A7 fused, rebatch-free image cross-attention core --------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(256) tpv_cross_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
-                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
-                                                             const float* __restrict__ uv, const unsigned char* __restrict__ vis,
-                                                             float* __restrict__ slots, int* __restrict__ count, int N, int Nv,
-                                                             int Hd, int Q, int L, int D) {
+// SPLIT sample-groups share one (query, head): group g takes pillar points d = g, g + SPLIT, ...  Planes with long
+// pillars (D = 48: only ~48 k items but 192 x cams samples each) would otherwise run as ~1 wave of long threads.
+template <int DH, int SPLIT>
+__global__ void __launch_bounds__(256, 5) tpv_cross_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes,
+                                                             const long long* __restrict__ lsi, const float* __restrict__ offsets,
+                                                             const float* __restrict__ logits, const float* __restrict__ uv,
+                                                             const unsigned char* __restrict__ vis, float* __restrict__ slots,
+                                                             int* __restrict__ count, int N, int Nv, int Hd, int Q, int L, int D) {
   constexpr int LPI = DH / 4;
+  constexpr int LANES = LPI * SPLIT;
   __shared__ Levels lv;
   load_levels(lv, shapes, lsi, L);
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long item = t / LPI;
-  int lc = (int)(t % LPI);
+  long long item = t / LANES;
+  const int li = (int)(t % LANES);
+  const int lc = li % LPI, sg = li / LPI;
   long long n_items = (long long)Q * Hd;
   bool live = item < n_items;
   if (!live) item = n_items - 1;
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(256) tpv_cross_attn_kernel(const float* __rest
   const float* op = offsets + item * (long long)LD * 2;
   const float* lg = logits + item * (long long)LD;
   float mx, inv_sum;
-  softmax_stats<LPI>(lg, LD, lc, mx, inv_sum);
+  softmax_stats<LANES>(lg, LD, li, mx, inv_sum);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   for (int cam = 0; cam < N; ++cam) {
@@ -216,22 +220,27 @@ __global__ void __launch_bounds__(256) tpv_cross_attn_kernel(const float* __rest
     float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int l = 0; l < L; ++l) {
       const int Hl = lv.h[l], Wl = lv.w[l];
-      const float fw = (float)Wl, fh = (float)Hl;
+      const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
       const float* vbase = value + (((long long)cam * Nv + lv.start[l]) * Hd + h) * DH + lc * 4;
 #pragma unroll 4
-      for (int d = 0; d < D; ++d) {
+      for (int d = sg; d < D; d += SPLIT) {
         float2 r = __ldg(reinterpret_cast<const float2*>(uvp) + d);
         float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * D + d);
-        float aw = expf(__ldg(lg + l * D + d) - mx) * inv_sum;
-        // image_cross_attention.py:326-328: ref + offset / (w_l, h_l)
-        float4 s = bilinear4(vbase, pstride, Hl, Wl, r.x + o.x / fw, r.y + o.y / fh);
+        float aw = __expf(__ldg(lg + l * D + d) - mx) * inv_sum;
+        // image_cross_attention.py:326-328: ref + offset / (w_l, h_l)   (reciprocal multiply: <= 1 ulp from the division)
+        float4 s = bilinear4(vbase, pstride, Hl, Wl, fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y));
         part.x = fmaf(aw, s.x, part.x); part.y = fmaf(aw, s.y, part.y);
         part.z = fmaf(aw, s.z, part.z); part.w = fmaf(aw, s.w, part.w);
       }
     }
     acc.x += part.x; acc.y += part.y; acc.z += part.z; acc.w += part.w;  // :129-131, camera order
   }
-  if (!live) return;
+#pragma unroll
+  for (int s = LPI; s < LANES; s <<= 1) {   // fold the sample groups
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, s); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, s);
+  }
+  if (!live || sg != 0) return;
   float c = (float)max(cnt, 1);  // :133-136
   acc.x /= c; acc.y /= c; acc.z /= c; acc.w /= c;
   *reinterpret_cast<float4*>(slots + item * DH + lc * 4) = acc;
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(256) tpv_cross_attn_kernel(const float* __rest
 
 // ---- A8 fused cross-view hybrid attention core -----------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(256) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+__global__ void __launch_bounds__(256, 5) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
                                                             const float* __restrict__ ref, float* __restrict__ out, int Nv, int Hd,
                                                             int Q, int L, int P) {
@@ -265,14 +274,14 @@ __global__ void __launch_bounds__(256) tpv_self_attn_kernel(const float* __restr
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 0; l < L; ++l) {
     const int Hl = lv.h[l], Wl = lv.w[l];
-    const float fw = (float)Wl, fh = (float)Hl;
+    const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
     const float* vbase = value + ((long long)lv.start[l] * Hd + h) * DH + lc * 4;
 #pragma unroll 4
     for (int p = 0; p < P; ++p) {
       float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l * P + p);
       float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * P + p);
-      float aw = expf(__ldg(lg + l * P + p) - mx) * inv_sum;
-      float4 s = bilinear4(vbase, pstride, Hl, Wl, r.x + o.x / fw, r.y + o.y / fh);  // cross_view_hybrid_attention.py:97-99
+      float aw = __expf(__ldg(lg + l * P + p) - mx) * inv_sum;
+      float4 s = bilinear4(vbase, pstride, Hl, Wl, fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y));  // cross_view_hybrid_attention.py:97-99
       acc.x = fmaf(aw, s.x, acc.x); acc.y = fmaf(aw, s.y, acc.y);
       acc.z = fmaf(aw, s.z, acc.z); acc.w = fmaf(aw, s.w, acc.w);
     }
@@ -423,12 +432,15 @@ extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spat
   if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
   const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
-  long long threads = (long long)Q * Hd * (Dh / 4);
+  const int split = D >= 32 ? 4 : (D >= 16 ? 2 : 1);
+  long long threads = (long long)Q * Hd * (Dh / 4) * split;
   unsigned grid = (unsigned)ceil_div64(threads, 256);
   ProfScope prof(2, st);
-  SO_DISPATCH_DH(Dh,
-                 (tpv_cross_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)),
-                 (tpv_cross_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)));
+#define SO_CROSS(DHV, SP) tpv_cross_attn_kernel<DHV, SP><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)
+  if (Dh == 16) { if (split == 4) SO_CROSS(16, 4); else if (split == 2) SO_CROSS(16, 2); else SO_CROSS(16, 1); }
+  else if (Dh == 32) { if (split == 4) SO_CROSS(32, 4); else if (split == 2) SO_CROSS(32, 2); else SO_CROSS(32, 1); }
+  else return SO_ERR_UNSUPPORTED;
+#undef SO_CROSS
   note_launch(1);
   return check_launch();
 }

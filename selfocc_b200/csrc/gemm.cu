@@ -43,7 +43,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D row-major fp32 matrix [rows, cols] (cols contiguous), box = [box_rows x 32 floats], 128-byte swizzle, zero OOB fill
-static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows) {
+static int make_tmap(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int box_rows) {  // box = [box_rows x 32]
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return SO_ERR_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -87,6 +87,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA prefetch of one box into L2 only: raises the bytes in flight beyond what the shared-memory ring can hold
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(smem_u32(src))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -154,6 +166,220 @@ struct GemmSmem {
   static constexpr int bars = b_lo + kChunkAtoms * kMaxBN * 128;
   static constexpr int total = bars + 64;
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised pipeline (one CTA per SM, 12 warps):
+//   warp 0      TMA producer   W tile (hi, lo; all K) once per CTA, then X atoms [128 x 32] into a ring of stages
+//   warp 1      MMA issuer     per atom: 3 products x 4 k-steps of tcgen05.mma.kind::tf32 into one of 2 TMEM accumulators
+//   warps 4-7   converters     split each raw X atom into hi (in place) and lo (second buffer), fence.proxy.async
+//   warps 8-11  epilogue       tcgen05.ld -> bias / ReLU / residual -> per-warp smem transpose -> coalesced stores
+// A CTA owns ONE n-tile (its W tile stays resident in shared memory) and walks m-tiles, so the streamed traffic per
+// output tile is the X tile and the Y tile only -- the HBM-bound minimum for these K = 96 projections.
+// mbarriers: w_full | full[s] (TMA landed) -> conv[s] (split done) -> empty[s] (MMAs retired) | tmem_full[a] / tmem_empty[a].
+constexpr int kStageBytes = 2 * kAtomBytesA;        // raw/hi atom + lo atom
+constexpr int kEpiWarpBytes = 32 * 128;             // per-warp TMA-store staging tile: 32 rows x 32 floats, 128B-swizzled
+constexpr int kPipeThreads = 384;
+constexpr int kMaxStages = 4;
+
+struct PipeCfg {
+  int BN, KA, stages;       // n-tile width, atoms along K (K / 32), ring depth
+  int w_bytes;              // resident W bytes = 2 * KA * BN * 128
+  int smem;                 // dynamic shared memory request (incl. 1 KB alignment slack)
+};
+
+static PipeCfg make_pipe_cfg(int N, int K) {
+  PipeCfg c;
+  c.BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
+  c.KA = K / kAtomK;
+  c.w_bytes = 2 * c.KA * c.BN * 128;
+  const int fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
+  const int budget = 227 * 1024 - 1024 - fixed;
+  c.stages = budget / kStageBytes;
+  if (c.stages > kMaxStages) c.stages = kMaxStages;
+  c.smem = fixed + c.stages * kStageBytes + 1024;
+  return c;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 1)
+linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                          const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_y,
+                          const float* __restrict__ bias, const float* __restrict__ residual, long long M, int N, int BN, int KA,
+                          int stages, int n_tiles, int m_tiles, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_bytes = 2 * KA * BN * 128;
+  uint8_t* w_hi = sm;
+  uint8_t* w_lo = sm + KA * BN * 128;
+  uint8_t* ring = sm + w_bytes;                                   // stages x [hi 16 KB | lo 16 KB], 1 KB aligned
+  uint8_t* epi = ring + stages * kStageBytes;                     // 4 x 4 KB, 1 KB aligned (swizzle atoms)
+  float* bias_s = reinterpret_cast<float*>(epi + 4 * kEpiWarpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kMaxBN);
+  uint64_t* w_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* conv = full + kMaxStages;
+  uint64_t* empty = conv + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int group = blockIdx.x / n_tiles, n_groups = gridDim.x / n_tiles;
+  const int n0 = n_tile * BN;
+
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)w_bytes);
+      for (int a = 0; a < KA; ++a) {
+        tma_load_2d(w_hi + a * BN * 128, &map_whi, a * kAtomK, n0, w_full);
+        tma_load_2d(w_lo + a * BN * 128, &map_wlo, a * kAtomK, n0, w_full);
+      }
+      int s = 0; uint32_t ph = 0;
+      constexpr int kPrefetchTiles = 4;                 // X tiles requested into L2 ahead of the smem ring
+      for (int p = 0; p < kPrefetchTiles; ++p) {
+        int mt = group + p * n_groups;
+        if (mt < m_tiles)
+          for (int a = 0; a < KA; ++a) tma_prefetch_l2_2d(&map_x, a * kAtomK, mt * kBM);
+      }
+      for (int mt = group; mt < m_tiles; mt += n_groups) {
+        const int mt_pf = mt + kPrefetchTiles * n_groups;
+        if (mt_pf < m_tiles)
+          for (int a = 0; a < KA; ++a) tma_prefetch_l2_2d(&map_x, a * kAtomK, mt_pf * kBM);
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, (uint32_t)kAtomBytesA);
+          tma_load_2d(ring + s * kStageBytes, &map_x, a * kAtomK, mt * kBM, full + s);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      mbar_wait(w_full, 0);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo);
+      for (int mt = group; mt < m_tiles; mt += n_groups) {
+        mbar_wait(tmem_empty + acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        uint32_t accum = 0;
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait(conv + s, ph);
+          tc_fence_after();
+          const uint32_t ahi = smem_u32(ring + s * kStageBytes), alo = ahi + kAtomBytesA;
+          const uint32_t bhi = whi + a * BN * 128, blo = wlo + a * BN * 128;
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t ab = prod == 1 ? alo : ahi;
+            const uint32_t bb = prod == 2 ? blo : bhi;
+#pragma unroll
+            for (int k = 0; k < kAtomK / 8; ++k) {
+              umma_tf32(d_tmem, make_desc(ab + k * 32), make_desc(bb + k * 32), idesc, accum);
+              accum = 1u;
+            }
+          }
+          umma_commit(empty + s);                       // stage reusable once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tmem_full + acc);                   // accumulator complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== converters: X = hi + lo =====
+    const int ct = tid - 128;
+    int s = 0; uint32_t ph = 0;
+    for (int mt = group; mt < m_tiles; mt += n_groups) {
+      for (int a = 0; a < KA; ++a) {
+        mbar_wait(full + s, ph);
+        float4* hi = reinterpret_cast<float4*>(ring + s * kStageBytes);
+        float4* lo = reinterpret_cast<float4*>(ring + s * kStageBytes + kAtomBytesA);
+#pragma unroll
+        for (int i = 0; i < kAtomBytesA / 16 / 128; ++i) {
+          float4 v = hi[ct + i * 128], h, l;
+          h.x = tf32_rn(v.x); l.x = v.x - h.x;
+          h.y = tf32_rn(v.y); l.y = v.y - h.y;
+          h.z = tf32_rn(v.z); l.z = v.z - h.z;
+          h.w = tf32_rn(v.w); l.w = v.w - h.w;
+          hi[ct + i * 128] = h;
+          lo[ct + i * 128] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(conv + s);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: TMEM -> registers (+bias, ReLU, +residual) -> swizzled smem tile -> TMA store =====
+    const int q = warp & 3;                              // TMEM lane quarter of this warp
+    uint8_t* tile = epi + q * kEpiWarpBytes;
+    for (int i = tid - 256; i < BN; i += 128) bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int mt = group; mt < m_tiles; mt += n_groups) {
+      mbar_wait(tmem_full + acc, acc_ph);
+      tc_fence_after();
+      const long long gr = (long long)mt * kBM + q * 32 + lane;      // this thread's output row
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), r);
+        if (lane == 0) tma_store_wait_read();             // previous TMA store has finished reading the tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+          float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
+                                 __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (residual) {
+            const int gc = n0 + c0 + 4 * j;
+            if (gr < M && gc + 3 < N) {
+              float4 rr = __ldg(reinterpret_cast<const float4*>(residual + gr * N + gc));
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            } else if (gr < M) {
+              if (gc < N) v.x += __ldg(residual + gr * N + gc);
+              if (gc + 1 < N) v.y += __ldg(residual + gr * N + gc + 1);
+              if (gc + 2 < N) v.z += __ldg(residual + gr * N + gc + 2);
+            }
+          }
+          // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        // TMA clips rows >= M and columns >= N; chunks that start beyond this n-tile's width are skipped
+        if (lane == 0 && n0 + c0 < N) tma_store_2d(&map_y, tile, n0 + c0, mt * kBM + q * 32);
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
@@ -307,27 +533,34 @@ extern "C" int so_split_tf32(const float* w, float* hi, float* lo, int64_t n, vo
 extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                                 float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
   if (!x || !w_hi || !w_lo || !y || M < 0 || N < 1 || K < 1) return SO_ERR_INVALID_ARG;
-  if (K % (kChunkAtoms * kAtomK) != 0) return SO_ERR_UNSUPPORTED;                 // K multiple of 96
+  if (K % (kChunkAtoms * kAtomK) != 0 || K > 192) return SO_ERR_UNSUPPORTED;      // K = 96 or 192
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15)
     return SO_ERR_INVALID_ARG;                                                    // TMA needs 16-byte aligned bases
   if (M == 0) return SO_OK;
   if (M > 0x7fffffffLL) return SO_ERR_UNSUPPORTED;
-  int BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
+  PipeCfg cfg = make_pipe_cfg(N, K);
+  if (cfg.stages < 2) return SO_ERR_UNSUPPORTED;
   CUtensorMap mx, mhi, mlo;
   int rc;
   if ((rc = make_tmap(&mx, x, M, K, kBM))) return rc;
-  if ((rc = make_tmap(&mhi, w_hi, N, K, BN))) return rc;
-  if ((rc = make_tmap(&mlo, w_lo, N, K, BN))) return rc;
-  static bool attr_set = false;
-  const int smem = GemmSmem::total + 1024;
-  if (!attr_set) {
-    if ((rc = check_cuda(cudaFuncSetAttribute(linear_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)))) return rc;
-    attr_set = true;
+  if ((rc = make_tmap(&mhi, w_hi, N, K, cfg.BN))) return rc;
+  if ((rc = make_tmap(&mlo, w_lo, N, K, cfg.BN))) return rc;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) || (N % 4)) return SO_ERR_UNSUPPORTED;   // TMA store: 16-byte aligned rows
+  CUtensorMap my;
+  if ((rc = make_tmap(&my, y, M, N, 32))) return rc;                                 // store box: 32 rows x 32 floats
+  static int smem_set = 0;
+  if (smem_set < cfg.smem) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(linear_3xtf32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
+    smem_set = 227 * 1024;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)ceil_div64(M, kBM), (unsigned)ceil_div64(N, BN));
+  const int n_tiles = (int)ceil_div64(N, cfg.BN), m_tiles = (int)ceil_div64(M, kBM);
+  int groups = kNumSMs / n_tiles;
+  if (groups < 1) groups = 1;
+  if (groups > m_tiles) groups = m_tiles;
   ProfScope prof(8, st);
-  linear_3xtf32_kernel<<<grid, kGemmThreads, smem, st>>>(mx, mhi, mlo, bias, residual, y, (long long)M, N, K, BN, relu);
+  linear_3xtf32_pipe_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
+                                                                            cfg.KA, cfg.stages, n_tiles, m_tiles, relu);
   note_launch(1);
   return check_launch();
 }

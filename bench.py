@@ -166,6 +166,10 @@ def run_b200(args):
         return all_gather_rays(packed, world * rays_per_frame)     # the one collective (frames are equal-sized slices)
 
     def timed(fn, K, W, sampler=None):
+        if sampler:
+            sampler.start()                                        # nvidia-smi needs ~100s of ms to start: sample from warm-up on
+            for _ in range(20):                                    # extra untimed steps so the clocks are sampled under load
+                fn()
         for _ in range(W):
             flush.zero_()
             fn()
@@ -173,8 +177,6 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
         evs = []
         l0 = _lib.launch_count()
         _lib.profile_reset()

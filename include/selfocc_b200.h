@@ -202,6 +202,11 @@ int so_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* str
 int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 
+/* A9  y = LayerNorm(x [+ add]) over the last dimension C (nn.LayerNorm(C), biased variance, eps inside the sqrt),
+ * replaces the norm steps of TPVFormerLayer (tpvformer_encoder_layer.py:185-196).  x, add, y [rows, C]; C <= 256. */
+int so_layer_norm(const float* x, const float* add, const float* gamma, const float* beta, float* y, int64_t rows,
+                  int32_t C, float eps, void* stream);
+
 /* A4  projection of pillar reference points into the cameras.  Replaces point_sampling
  * (model/encoder/bevformer/utils.py:116-206, no post_rots / focal_ratios branch).
  *   ref_3d [D, Q, 3] metres, lidar2img [N, 4, 4], img_h/img_w = metas[0]['img_shape']

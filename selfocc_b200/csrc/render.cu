@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
   const float gw0 = fmaf(o[0] - V.ax[1].start, kw0, V.ax[1].offset), gdw = d[0] * kw0;
   const float gd0 = fmaf(o[2] - V.ax[2].start, kd0, V.ax[2].offset), gdd = d[2] * kd0;
   const int Hm1 = V.H - 1, Wm1 = V.W - 1, Zm1 = V.Z - 1;
+  const bool anneal_done = P.cos_anneal == 1.0f;   // -(relu(-tc)) == min(tc, 0)
 
   float T = 1.0f, acc = 0.f, dsum = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
   float best = -INFINITY, best_mid = 0.f;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     float gx = dgw * kw, gy = dgh * kh, gz = dgd * kd;  // d sdf / d metre (x, y, z)
     // NeuS alpha (upstream SDFField.get_alpha)
     float tc = d[0] * gx + d[1] * gy + d[2] * gz;
-    float ic = -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
+    float ic = anneal_done ? fminf(tc, 0.f)
+                           : -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
     float alpha = neus_alpha(sdf, ic * delta * 0.5f, P.inv_s);
     float w = alpha * T;
     T *= (1.0f - alpha + 1e-7f);

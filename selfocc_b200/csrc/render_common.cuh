@@ -174,9 +174,8 @@ __device__ __forceinline__ void gather_feat(const VolumeDev& v, const Taps& t, i
 
 // sigmoid via one ex2.approx + one rcp.approx (abs error ~1e-7): exp(-|x|) never overflows
 __device__ __forceinline__ float sigmoid_fast(float x) {
-  float e = __expf(-fabsf(x));
-  float s = __fdividef(1.0f, 1.0f + e);
-  return x >= 0.f ? s : e * s;
+  // exp(-x) may overflow to +inf for very negative x; rcp.approx(inf) = 0 is the correct limit
+  return __fdividef(1.0f, 1.0f + __expf(-x));
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) {
   float e = expf(-fabsf(x));

@@ -457,7 +457,13 @@ class TPVFormerLayer(nn.Module):
                 attn_i += 1
                 identity = query
             elif op == 'norm':
-                query = torch.split(self.norms[norm_i](torch.cat(query, dim=1)), split, 1)
+                q = torch.cat(query, dim=1)
+                ln = self.norms[norm_i]
+                if q.is_cuda and q.dtype == torch.float32 and q.shape[-1] <= 256 and not _needs_grad(q, ln.weight):
+                    q = ops.layer_norm(q.contiguous(), ln.weight.detach(), ln.bias.detach(), ln.eps)
+                else:
+                    q = ln(q)
+                query = torch.split(q, split, 1)
                 norm_i += 1
             elif op == 'cross_attn':
                 query = self.attentions[attn_i](query, key, value, identity if self.pre_norm else None,

@@ -390,3 +390,14 @@ def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None):
 
 def linear_supported(K):
     return K % 96 == 0
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, add=None):
+    """y = LayerNorm(x [+ add]) over the last dim (fp32), one warp per row."""
+    lib = _lib.load()
+    _chk(x, name='x'); _chk(add, name='add'); _chk(gamma, name='weight'); _chk(beta, name='bias')
+    Cn = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.check(lib.so_layer_norm(_p(x), _p(add), _p(gamma), _p(beta), _p(y), x.numel() // Cn, Cn, float(eps), _stream()),
+               'so_layer_norm')
+    return y

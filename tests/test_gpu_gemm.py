@@ -34,3 +34,19 @@ def test_linear_3xtf32_matches_fp64(M, N, K, relu, res):
     scale = ref.abs().max().item()
     print('3xTF32 GEMM M=%d N=%d K=%d: max abs err %.3e (cuBLAS fp32 %.3e), |y|max %.2f' % (M, N, K, err, err_cublas, scale))
     assert err < 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize('rows,C,with_add', [(1000, 96, False), (81983, 96, True), (77, 128, False), (5, 200, True)])
+def test_layer_norm_matches_torch(rows, C, with_add):
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    from selfocc_b200 import ops
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, C, generator=g) * 3 + 1).to(dev)
+    a = torch.randn(rows, C, generator=g).to(dev) if with_add else None
+    w, b = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    y = ops.layer_norm(x, w, b, 1e-5, add=a)
+    xin = x if a is None else x + a
+    ref = torch.nn.functional.layer_norm(xin.double(), (C,), w.double(), b.double(), 1e-5)
+    assert torch.allclose(y.double(), ref, atol=2e-5, rtol=1e-5)

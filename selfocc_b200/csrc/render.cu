@@ -66,7 +66,9 @@ int launch_depth_bounds(const RayDev& R, const RenderDev& P, float* ws, cudaStre
 }
 
 
-template <bool HAS_RGB, bool HAS_SEM>
+// FAST = affine metre->grid map, power-of-two S, cos-anneal finished, mid-point anchor (every shipped eval config):
+// the uniform branches for the general cases are compiled out.
+template <bool HAS_RGB, bool HAS_SEM, bool FAST>
 __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                            const float* __restrict__ bkgd_rand, float* __restrict__ depth,
                                                            float* __restrict__ max_depth, long long* __restrict__ max_idx,
@@ -82,18 +84,19 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
 
   const int S = P.S;
   const float step = 1.0f / (float)S;
-  const bool pow2 = (S & (S - 1)) == 0;            // then i * (1/S) is exact and equals torch.linspace bit for bit
+  const bool pow2 = FAST || (S & (S - 1)) == 0;    // then i * (1/S) is exact and equals torch.linspace bit for bit
   const float eps = 1.1920928955078125e-07f;       // torch.finfo(float32).eps (neus_head.py:431)
   const float eps_len = eps * nrm;                 // delta / nrm < eps  <=>  delta < eps * nrm
   // metre -> grid is affine per axis when the mapping has no outer ring (every shipped config):
   // g(t) = g0 + gd * t along the ray, one FMA per axis per sample
-  const bool affine = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f;
+  const bool affine = FAST || (V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f);
   const float kh0 = V.ax[0].k0, kw0 = V.ax[1].k0, kd0 = V.ax[2].k0;
   const float gh0 = fmaf(o[1] - V.ax[0].start, kh0, V.ax[0].offset), gdh = d[1] * kh0;
   const float gw0 = fmaf(o[0] - V.ax[1].start, kw0, V.ax[1].offset), gdw = d[0] * kw0;
   const float gd0 = fmaf(o[2] - V.ax[2].start, kd0, V.ax[2].offset), gdd = d[2] * kd0;
   const int Hm1 = V.H - 1, Wm1 = V.W - 1, Zm1 = V.Z - 1;
-  const bool anneal_done = P.cos_anneal == 1.0f;   // -(relu(-tc)) == min(tc, 0)
+  const bool anneal_done = FAST || P.cos_anneal == 1.0f;   // -(relu(-tc)) == min(tc, 0)
+  const float k_log2 = P.inv_s * 1.4426950408889634f;       // inv_s * log2(e)
 
   float T = 1.0f, acc = 0.f, dsum = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
   float best = -INFINITY, best_mid = 0.f;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     float e1 = edge_t(b1, tn, tf);
     float mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
     float delta = __fsub_rn(e1, e0);
-    float tq = P.anchor_mid ? mid : e0;
+    float tq = (FAST || P.anchor_mid) ? mid : e0;
     e0 = e1;
     float gh, gw, gd, kh = kh0, kw = kw0, kd = kd0;
     if (affine) {
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     float tc = d[0] * gx + d[1] * gy + d[2] * gz;
     float ic = anneal_done ? fminf(tc, 0.f)
                            : -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
-    float alpha = neus_alpha(sdf, ic * delta * 0.5f, P.inv_s);
+    float alpha = neus_alpha_log2(sdf * k_log2, ic * (delta * (0.5f * k_log2)));
     float w = alpha * T;
     T *= (1.0f - alpha + 1e-7f);
     acc += w;
@@ -251,12 +254,13 @@ extern "C" int so_render_infer(const float* vol_sdf, const float* vol_feat, cons
   unsigned grid = (unsigned)ceil_div64(rd->ray_count, 128);
   ProfScope prof(0, st);
   long long* midx = reinterpret_cast<long long*>(max_idx);
-  if (want_sem)
-    render_infer_kernel<true, true><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
-  else if (want_rgb)
-    render_infer_kernel<true, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
-  else
-    render_infer_kernel<false, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem);
+  const bool fast = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f && (P.S & (P.S - 1)) == 0 &&
+                    P.cos_anneal == 1.0f && P.anchor_mid;
+#define SO_RENDER(RGB, SEM, F) render_infer_kernel<RGB, SEM, F><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem)
+  if (want_sem) { if (fast) SO_RENDER(true, true, true); else SO_RENDER(true, true, false); }
+  else if (want_rgb) { if (fast) SO_RENDER(true, false, true); else SO_RENDER(true, false, false); }
+  else { if (fast) SO_RENDER(false, false, true); else SO_RENDER(false, false, false); }
+#undef SO_RENDER
   note_launch(1);
   return check_launch();
 }

@@ -202,6 +202,17 @@ __device__ __forceinline__ float neus_alpha(float sdf, float half, float inv_s) 
   return __saturatef(__fdividef(diff + 1e-5f, pa + 1e-5f));
 }
 
+// The same alpha with every exponential taken in base 2: s2 = sdf * inv_s * log2(e), h2 = half * inv_s * log2(e) (<= 0),
+// so each logistic is one ex2.approx + one rcp.approx with no scaling multiply in front.
+__device__ __forceinline__ float neus_alpha_log2(float s2, float h2) {
+  float pa = __fdividef(1.0f, 1.0f + exp2f(h2 - s2));           // Phi(prev) = 1 / (1 + 2^-(s2 - h2))
+  float qb = __fdividef(1.0f, 1.0f + exp2f(s2 + h2));           // Phi(-next)
+  float x = h2 * (-2.0f * 0.6931471805599453f);                 // a - b in natural units (>= 0)
+  float ser = x * (1.0f - x * 0.5f * (1.0f - x * (1.0f / 3.0f) * (1.0f - x * 0.25f * (1.0f - x * 0.2f))));
+  float omen = x < 0.125f ? ser : 1.0f - exp2f(2.0f * h2);
+  return __saturatef(__fdividef(fmaf(pa * qb, omen, 1e-5f), pa + 1e-5f));
+}
+
 constexpr float kC0 = 0.28209479177387814f;  // sh_render.py:4
 
 constexpr int kMaxSem = 32;  // rendered semantic classes (n_feat - 3) supported per ray

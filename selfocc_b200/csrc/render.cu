@@ -108,14 +108,28 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     for (int i = 0; i < kMaxSem; ++i) sem[i] = 0.f;
 
   float e0 = edge_t(bin_edge01(0, S, step), tn, tf);
+  // FAST path: uniform bins, so mid_s = tn + (s + 1/2) * span / S and delta = span / S is constant along the ray
+  // (within 1-2 ulp of the reference's edge arithmetic, far inside the 1e-5 tolerance of depth / max-depth)
+  const float span = tf - tn;
+  const float delta_c = span * step;
+  const float h_const = delta_c * (0.5f * k_log2);
+  float bm = 0.5f * step;
 #pragma unroll 2
   for (int s = 0; s < S; ++s) {
-    float b1 = pow2 ? (float)(s + 1) * step : bin_edge01(s + 1, S, step);
-    float e1 = edge_t(b1, tn, tf);
-    float mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
-    float delta = __fsub_rn(e1, e0);
-    float tq = (FAST || P.anchor_mid) ? mid : e0;
-    e0 = e1;
+    float mid, delta, tq;
+    if (FAST) {
+      mid = fmaf(bm, span, tn);
+      bm += step;
+      delta = delta_c;
+      tq = mid;
+    } else {
+      float b1 = pow2 ? (float)(s + 1) * step : bin_edge01(s + 1, S, step);
+      float e1 = edge_t(b1, tn, tf);
+      mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
+      delta = __fsub_rn(e1, e0);
+      tq = P.anchor_mid ? mid : e0;
+      e0 = e1;
+    }
     float gh, gw, gd, kh = kh0, kw = kw0, kd = kd0;
     if (affine) {
       gh = fmaf(gdh, tq, gh0); gw = fmaf(gdw, tq, gw0); gd = fmaf(gdd, tq, gd0);
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     float tc = d[0] * gx + d[1] * gy + d[2] * gz;
     float ic = anneal_done ? fminf(tc, 0.f)
                            : -(fmaxf(fmaf(-tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-tc, 0.f) * P.cos_anneal);
-    float alpha = neus_alpha_log2(sdf * k_log2, ic * (delta * (0.5f * k_log2)));
+    float alpha = neus_alpha_log2(sdf * k_log2, ic * (FAST ? h_const : delta * (0.5f * k_log2)));
     float w = alpha * T;
     T *= (1.0f - alpha + 1e-7f);
     acc += w;
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     n0 = fmaf(wn, gx, n0); n1 = fmaf(wn, gy, n1); n2 = fmaf(wn, gz, n2);
     // max-depth candidate (neus_head.py:430-438): first maximum of w / clamp(delta', eps) with w := 0 where delta' < eps;
     // delta' = delta / |dir| and |dir| is constant along the ray, so the argmax is taken over w / delta
-    float cand = delta < eps_len ? 0.f : __fdividef(w, delta);
+    float cand = FAST ? w : (delta < eps_len ? 0.f : __fdividef(w, delta));   // FAST: delta is a positive per-ray constant
     if (cand > best) { best = cand; best_i = s; best_mid = mid; }
     if (HAS_RGB) {
       float f[3];
@@ -171,6 +185,7 @@ __global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R
     }
   }
   if (!valid) return;
+  if (FAST && delta_c < eps_len) { best_i = 0; best_mid = fmaf(0.5f * step, span, tn); }   // all candidates are 0: first index
 
   long long chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
   float lo = __ldg(ws + 2 * chunk), hi = __ldg(ws + 2 * chunk + 1);

@@ -31,34 +31,58 @@ struct Sample {
   float kh, kw, kd;
 };
 
-__device__ __forceinline__ float sigmoid_train(float x) {
-  float e = __expf(-fabsf(x));
-  float r = __fdividef(1.0f, 1.0f + e);
-  return x >= 0.f ? r : e * r;
+// Per-ray constants of the training kernels (hoisted out of the per-sample work)
+struct RayCtx {
+  float o[3], d[3], nrm, inv_nrm, tn, tf;
+  float gh0, gdh, gw0, gdw, gd0, gdd;   // affine grid-space ray (valid when the mapping has no outer ring)
+  bool affine;
+  const float* u;                       // this ray's jitter row or nullptr
+};
+
+__device__ __forceinline__ void make_ctx(const VolumeDev& V, const RayDev& R, const RenderDev& P, long long gid, RayCtx& c) {
+  make_ray(R, gid, c.o, c.d, c.nrm);
+  slab(P, c.o, c.d, c.tn, c.tf);
+  c.inv_nrm = 1.0f / c.nrm;
+  c.affine = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f;
+  c.gh0 = fmaf(c.o[1] - V.ax[0].start, V.ax[0].k0, V.ax[0].offset); c.gdh = c.d[1] * V.ax[0].k0;
+  c.gw0 = fmaf(c.o[0] - V.ax[1].start, V.ax[1].k0, V.ax[1].offset); c.gdw = c.d[0] * V.ax[1].k0;
+  c.gd0 = fmaf(c.o[2] - V.ax[2].start, V.ax[2].k0, V.ax[2].offset); c.gdd = c.d[2] * V.ax[2].k0;
+  c.u = P.jitter ? P.jitter + gid * (long long)(P.S + 1) : nullptr;
 }
 
-__device__ __forceinline__ void eval_sample(const VolumeDev& V, const RenderDev& P, const float o[3], const float d[3], float tn,
-                                            float tf, int s, const float* __restrict__ u, Sample& q) {
+// one sample of one ray (lane = sample): geometry + field + alpha.  `s` must be < S.  Edges are shared between
+// neighbouring lanes with one shuffle (lane 31 computes its own right edge).
+__device__ __forceinline__ void eval_sample(const VolumeDev& V, const RenderDev& P, const RayCtx& c, int s, int lane, Sample& q) {
   const int S = P.S;
   const float step = 1.0f / (float)S;
-  float e0 = edge_t(bin_edge01_jit(s, S, step, u), tn, tf);
-  float e1 = edge_t(bin_edge01_jit(s + 1, S, step, u), tn, tf);
+  float e0 = edge_t(bin_edge01_jit(s, S, step, c.u), c.tn, c.tf);
+  float e1 = __shfl_down_sync(0xffffffffu, e0, 1);
+  if (lane == 31 || s + 1 >= S) e1 = edge_t(bin_edge01_jit(min(s + 1, S), S, step, c.u), c.tn, c.tf);
   q.mid = __fmul_rn(__fadd_rn(e0, e1), 0.5f);
   q.delta = __fsub_rn(e1, e0);
   float tq = P.anchor_mid ? q.mid : e0;
-  float x = fmaf(d[0], tq, o[0]), y = fmaf(d[1], tq, o[1]), z = fmaf(d[2], tq, o[2]);
-  float gh = axis_m2g(V.ax[0], y, q.kh), gw = axis_m2g(V.ax[1], x, q.kw), gd = axis_m2g(V.ax[2], z, q.kd);
+  float gh, gw, gd;
+  if (c.affine) {
+    gh = fmaf(c.gdh, tq, c.gh0); gw = fmaf(c.gdw, tq, c.gw0); gd = fmaf(c.gdd, tq, c.gd0);
+    q.kh = V.ax[0].k0; q.kw = V.ax[1].k0; q.kd = V.ax[2].k0;
+  } else {
+    float x = fmaf(c.d[0], tq, c.o[0]), y = fmaf(c.d[1], tq, c.o[1]), z = fmaf(c.d[2], tq, c.o[2]);
+    gh = axis_m2g(V.ax[0], y, q.kh); gw = axis_m2g(V.ax[1], x, q.kw); gd = axis_m2g(V.ax[2], z, q.kd);
+  }
   q.t = make_taps(V, gh, gw, gd);
   float dgh, dgw, dgd;
-  gather_sdf(V, q.t, q.sdf, dgh, dgw, dgd);
+  const bool interior = (unsigned)q.t.h0 < (unsigned)(V.H - 1) && (unsigned)q.t.w0 < (unsigned)(V.W - 1) &&
+                        (unsigned)q.t.z0 < (unsigned)(V.Z - 1);
+  if (__all_sync(0xffffffffu, interior)) gather_sdf_interior(V, q.t.h0, q.t.w0, q.t.z0, q.t.fh, q.t.fw, q.t.fz, q.sdf, dgh, dgw, dgd);
+  else gather_sdf(V, q.t, q.sdf, dgh, dgw, dgd);
   q.gx = dgw * q.kw; q.gy = dgh * q.kh; q.gz = dgd * q.kd;
-  q.tc = d[0] * q.gx + d[1] * q.gy + d[2] * q.gz;
+  q.tc = c.d[0] * q.gx + c.d[1] * q.gy + c.d[2] * q.gz;
   float ic = -(fmaxf(fmaf(-q.tc, 0.5f, 0.5f), 0.f) * (1.0f - P.cos_anneal) + fmaxf(-q.tc, 0.f) * P.cos_anneal);
   q.half = ic * q.delta * 0.5f;
   float a = (q.sdf - q.half) * P.inv_s, b = (q.sdf + q.half) * P.inv_s;
-  q.pa = sigmoid_train(a);
-  q.pb = sigmoid_train(b);
-  float diff = q.pa * sigmoid_train(-b) * one_minus_exp_neg(-2.0f * q.half * P.inv_s);
+  q.pa = sigmoid_fast(a);
+  q.pb = sigmoid_fast(b);
+  float diff = q.pa * sigmoid_fast(-b) * one_minus_exp_neg(-2.0f * q.half * P.inv_s);
   q.alpha = __saturatef(__fdividef(diff + 1e-5f, q.pa + 1e-5f));
 }
 
@@ -106,10 +130,9 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
   const float eps = 1.1920928955078125e-07f;
   for (long long ray = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); ray < R.ray_count; ray += warps) {
     long long gid = R.ray_begin + ray;
-    float o[3], d[3], nrm, tn, tf;
-    make_ray(R, gid, o, d, nrm);
-    slab(P, o, d, tn, tf);
-    const float* u = P.jitter ? P.jitter + gid * (long long)(S + 1) : nullptr;
+    RayCtx c;
+    make_ctx(V, R, P, gid, c);
+    const float nrm = c.nrm, tf = c.tf;
     float carry = 1.0f, acc = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     float best = -INFINITY, best_ts = 0.f;
     int best_i = 0x7fffffff;
@@ -120,7 +143,7 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
       int s = k * 32 + lane;
       bool live = s < S;
       Sample q;
-      eval_sample(V, P, o, d, tn, tf, live ? s : S - 1, u, q);
+      eval_sample(V, P, c, live ? s : S - 1, lane, q);
       float alpha = live ? q.alpha : 0.f;
       float f = live ? (1.0f - alpha + 1e-7f) : 1.0f;
       float incl = warp_incl_prod(f, lane);
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
       float w = alpha * T;
       if (live) {
         long long oidx = ray * S + s;
-        float ts = q.mid / nrm, dl = q.delta / nrm;     // neus_head.py:571-577
+        float ts = q.mid * c.inv_nrm, dl = q.delta * c.inv_nrm;     // neus_head.py:571-577 (reciprocal multiply, <= 1 ulp)
         if (O.weights) O.weights[oidx] = w;
         if (O.ts) O.ts[oidx] = ts;
         if (O.deltas) O.deltas[oidx] = dl;
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
         if (O.eik) { O.eik[3 * oidx] = q.gx; O.eik[3 * oidx + 1] = q.gy; O.eik[3 * oidx + 2] = q.gz; }
         acc += w;
         dsum = fmaf(w, q.mid, dsum);
-        float cand = (dl < eps ? 0.f : w) / fmaxf(dl, eps);  // neus_head.py:579-587
+        float cand = (dl < eps ? 0.f : w) * __fdividef(1.0f, fmaxf(dl, eps));  // neus_head.py:579-587
         if (cand > best) { best = cand; best_i = s; best_ts = ts; }
         if (HAS_RGB) {
           float col[3], raw[3];
@@ -234,10 +257,10 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
   float g_invs_local = 0.f;
   for (long long ray = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); ray < R.ray_count; ray += warps) {
     long long gid = R.ray_begin + ray;
-    float o[3], d[3], nrm, tn, tf;
-    make_ray(R, gid, o, d, nrm);
-    slab(P, o, d, tn, tf);
-    const float* u = P.jitter ? P.jitter + gid * (long long)(S + 1) : nullptr;
+    RayCtx c;
+    make_ctx(V, R, P, gid, c);
+    const float nrm = c.nrm;
+    const float* d = c.d;
     // ---- pass 1: transmittance per sample, ray sums
     float Tk[kTrainMaxChunks], Ak[kTrainMaxChunks];
     float carry = 1.0f, acc = 0.f, dsum = 0.f;
@@ -247,7 +270,7 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
       int s = k * 32 + lane;
       bool live = s < S;
       Sample q;
-      eval_sample(V, P, o, d, tn, tf, live ? s : S - 1, u, q);
+      eval_sample(V, P, c, live ? s : S - 1, lane, q);
       float alpha = live ? q.alpha : 0.f;
       float f = live ? (1.0f - alpha + 1e-7f) : 1.0f;
       float incl = warp_incl_prod(f, lane);
@@ -280,7 +303,7 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
       int s = kk * 32 + lane;
       bool live = s < S;
       Sample q;
-      eval_sample(V, P, o, d, tn, tf, live ? s : S - 1, u, q);
+      eval_sample(V, P, c, live ? s : S - 1, lane, q);
       float T = Tk[kk], alpha = Ak[kk];
       float w = alpha * T;
       long long oidx = ray * S + (live ? s : S - 1);

@@ -241,11 +241,15 @@ def run_b200(args):
     dur = (r_ms / max(r_calls, 1)) * 1e-3
     achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
     flop_per_ray = 256 * 150.0                # SURVEY 8d estimate: ~150 flop per sample
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed `ncu --set full` capture
+    # (profiles/r1_step_kernels_ncu.txt: 10.03 MB read + 149.94 MB written); only valid for the default workload
+    traffic = 159.96e6 if args.workload == 'nuscenes_novel_depth_900x1600' else None
     roofline = {'kernel': 'render_infer_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': 'measured' if peaks else 'fallback',
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': 'measured' if peaks else 'fallback',
                 'launch_ms': dur * 1e3, 'algorithmic_bytes_per_launch': alg_bytes,
-                'note': 'inference render is ALU/L1-gather bound by construction (~600 flop/B, SURVEY 8d caveat): '
-                        'fp32 throughput estimate %.1f TFLOP/s' % (rays_per_frame * flop_per_ray / dur / 1e12 if dur > 0 else 0)}
+                'note': 'inference render is issue-slot/L1-gather bound by construction (~600 flop/B, SURVEY 8d caveat; ncu: '
+                        'smsp__issue_active 74%%, L1 hit 96%%, DRAM <1%%): fp32 throughput estimate %.1f TFLOP/s'
+                        % (rays_per_frame * flop_per_ray / dur / 1e12 if dur > 0 else 0)}
     breakdown = {k: round(v[0] / K, 4) for k, v in prof.items()}
     line = {'metric': 'rendered rays/sec (6-cam 900x1600)', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -7,6 +7,9 @@
 // bound, not HBM bound.
 #include "common.cuh"
 #include <math.h>
+#ifndef SO_ATTN_MIN_CTAS
+#define SO_ATTN_MIN_CTAS 5     // 48 registers; 6 (40 registers) spills more and measured slower
+#endif
 
 namespace so {
 
@@ -187,7 +190,7 @@ __device__ __forceinline__ void softmax_stats(const float* __restrict__ lg, int 
 // SPLIT sample-groups share one (query, head): group g takes pillar points d = g, g + SPLIT, ...  Planes with long
 // pillars (D = 48: only ~48 k items but 192 x cams samples each) would otherwise run as ~1 wave of long threads.
 template <int DH, int SPLIT>
-__global__ void __launch_bounds__(256, 5) tpv_cross_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes,
+__global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_cross_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes,
                                                              const long long* __restrict__ lsi, const float* __restrict__ offsets,
                                                              const float* __restrict__ logits, const float* __restrict__ uv,
                                                              const unsigned char* __restrict__ vis, float* __restrict__ slots,
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256, 5) tpv_cross_attn_kernel(const float* __r
 
 // ---- A8 fused cross-view hybrid attention core -----------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(256, 5) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+__global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
                                                             const float* __restrict__ ref, float* __restrict__ out, int Nv, int Hd,
                                                             int Q, int L, int P) {
@@ -290,38 +293,38 @@ __global__ void __launch_bounds__(256, 5) tpv_self_attn_kernel(const float* __re
 }
 
 // ---- A4 point_sampling (bevformer/utils.py:116-206) ---------------------------------------------------------
-// One thread per (camera, query); it walks the query's pillar of D reference points.  The projection uses
-// plain fp32 mul/add in a fixed left-to-right order (no FMA contraction): `mask` generates index lists.
+// One thread per (camera, query, pillar point): fully coalesced uv / mask stores.  The projection uses plain fp32
+// mul/add in a fixed left-to-right order (no FMA contraction): `mask` generates index lists.  `vis` (any over the
+// pillar) is zero-filled first and set with idempotent byte stores.
 __global__ void __launch_bounds__(256) point_sampling_kernel(const float* __restrict__ ref3d, const float* __restrict__ l2i,
                                                              int D, int Q, int N, float img_h, float img_w,
                                                              float* __restrict__ uv, unsigned char* __restrict__ mask,
                                                              unsigned char* __restrict__ vis) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= (long long)N * Q) return;
-  int cam = (int)(t / Q), q = (int)(t % Q);
-  float m[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) m[i] = __ldg(l2i + cam * 16 + i);
+  if (t >= (long long)N * Q * D) return;
+  int d = (int)(t % D);
+  long long cq = t / D;
+  int cam = (int)(cq / Q), q = (int)(cq % Q);
+  const float* m = l2i + cam * 16;
   const float eps = 1e-5f;
-  bool any = false;
-  for (int d = 0; d < D; ++d) {
-    const float* p = ref3d + ((long long)d * Q + q) * 3;
-    float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
-    float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
-    float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
-    bool ok = cz > eps;
-    float den = fmaxf(cz, eps);
-    float u = __fdiv_rn(__fdiv_rn(cx, den), img_w);
-    float v = __fdiv_rn(__fdiv_rn(cy, den), img_h);
-    ok = ok && (v > 0.f) && (v < 1.f) && (u < 1.f) && (u > 0.f);
-    long long o = ((long long)cam * Q + q) * D + d;
-    uv[2 * o] = u;
-    uv[2 * o + 1] = v;
-    if (mask) mask[o] = ok ? 1 : 0;
-    any = any || ok;
-  }
-  if (vis) vis[(long long)cam * Q + q] = any ? 1 : 0;
+  const float* p = ref3d + ((long long)d * Q + q) * 3;
+  float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+  float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 0), x), __fmul_rn(__ldg(m + 1), y)), __fmul_rn(__ldg(m + 2), z)), __ldg(m + 3));
+  float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 4), x), __fmul_rn(__ldg(m + 5), y)), __fmul_rn(__ldg(m + 6), z)), __ldg(m + 7));
+  float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__ldg(m + 8), x), __fmul_rn(__ldg(m + 9), y)), __fmul_rn(__ldg(m + 10), z)), __ldg(m + 11));
+  bool ok = cz > eps;
+  float den = fmaxf(cz, eps);
+  float u = __fdiv_rn(__fdiv_rn(cx, den), img_w);
+  float v = __fdiv_rn(__fdiv_rn(cy, den), img_h);
+  ok = ok && (v > 0.f) && (v < 1.f) && (u < 1.f) && (u > 0.f);
+  reinterpret_cast<float2*>(uv)[t] = make_float2(u, v);
+  if (mask) mask[t] = ok ? 1 : 0;
+  if (vis && ok) vis[cq] = 1;
+}
+
+__global__ void zero_bytes_kernel(unsigned char* p, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
 }
 
 // ---- A5 ordered index lists (nonzero) ---------------------------------------------------------------------
@@ -415,9 +418,13 @@ extern "C" int so_point_sampling(const float* ref_3d, const float* lidar2img, in
                                  float img_w, float* uv, uint8_t* mask, uint8_t* vis, void* stream) {
   if (!ref_3d || !lidar2img || !uv) return SO_ERR_INVALID_ARG;
   if (D < 1 || Q < 1 || N < 1 || !(img_h > 0.f) || !(img_w > 0.f)) return SO_ERR_INVALID_ARG;
-  long long n = (long long)N * Q;
-  point_sampling_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(ref_3d, lidar2img, D, Q, N, img_h, img_w,
-                                                                                         uv, mask, vis);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vis) {
+    zero_bytes_kernel<<<(unsigned)ceil_div64((long long)N * Q, 256), 256, 0, st>>>(vis, (long long)N * Q);
+    note_launch(1);
+  }
+  long long n = (long long)N * Q * D;
+  point_sampling_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(ref_3d, lidar2img, D, Q, N, img_h, img_w, uv, mask, vis);
   note_launch(1);
   return check_launch();
 }

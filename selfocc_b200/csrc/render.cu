@@ -7,6 +7,9 @@
 // decoded volume and the per-ray outputs are written fully coalesced.  The 256-sample compositing
 // recurrence is kept in registers in the reference's order (exclusive cumprod, first-max argmax).
 #include "render_common.cuh"
+#ifndef SO_RENDER_MIN_CTAS
+#define SO_RENDER_MIN_CTAS 8    // 64 registers, no spills (10 -> 48 registers spills inside the sample loop and is slower)
+#endif
 
 namespace so {
 
@@ -46,9 +49,11 @@ __global__ void __launch_bounds__(256) bounds_kernel(RayDev R, RenderDev P, floa
       mx = fmaxf(mx, __shfl_xor_sync(full, mx, s));
     }
     if ((threadIdx.x & 31) == 0 && mn != INFINITY) {
-      // all values are >= 0, so the int ordering equals the float ordering
-      atomicMin((int*)(ws + 2 * c0), __float_as_int(mn));
-      atomicMax((int*)(ws + 2 * c0 + 1), __float_as_int(mx));
+      // all values are >= 0, so the int ordering equals the float ordering.  Same-address atomics serialise in L2
+      // (~1 ns each): issue one only when it can still improve the current bound (monotone, so the race is benign).
+      volatile float* vw = ws;
+      if (mn < vw[2 * c0]) atomicMin((int*)(ws + 2 * c0), __float_as_int(mn));
+      if (mx > vw[2 * c0 + 1]) atomicMax((int*)(ws + 2 * c0 + 1), __float_as_int(mx));
     }
   } else if (ok) {
     atomicMin((int*)(ws + 2 * chunk), __float_as_int(mn));
@@ -69,7 +74,7 @@ int launch_depth_bounds(const RayDev& R, const RenderDev& P, float* ws, cudaStre
 // FAST = affine metre->grid map, power-of-two S, cos-anneal finished, mid-point anchor (every shipped eval config):
 // the uniform branches for the general cases are compiled out.
 template <bool HAS_RGB, bool HAS_SEM, bool FAST>
-__global__ void __launch_bounds__(128) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+__global__ void __launch_bounds__(128, SO_RENDER_MIN_CTAS) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                            const float* __restrict__ bkgd_rand, float* __restrict__ depth,
                                                            float* __restrict__ max_depth, long long* __restrict__ max_idx,
                                                            float* __restrict__ acc_out, float* __restrict__ normal_vis,

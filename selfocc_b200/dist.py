@@ -41,7 +41,7 @@ def render_sharded(head, metas, batch=0, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     sampler = head._sampler()
-    n_cam = len(metas[0][(head.img2lidar.trans_kw_eval if False else head.img2lidar.trans_kw)[0]])
+    n_cam = head.img2lidar.matrices(metas, torch.device('cpu')).shape[1]
     total = n_cam * sampler.ray_number
     begin, count = ray_slice(total, world, rank)
     out = head.render(metas=metas, batch=batch, ray_range=(begin, count))

@@ -148,3 +148,19 @@ def test_forward_occ_matches_oracle():
     assert torch.allclose(out['sdf'].cpu(), sdf.float(), atol=3e-5)
     assert torch.allclose(out['logits'].cpu(), sem.float(), atol=3e-5)
     assert out['sem'].dtype == torch.int64
+
+
+def test_render_sharded_single_process_equals_render():
+    """dist.render_sharded without a process group degenerates to the plain render (the 2-rank collective itself is
+    covered on CPU/gloo in tests/test_dist_cpu.py; slices of the flat ray order are covered in test_gpu_render.py)."""
+    model, cfg, margs, rng, metas, feats, l2i, i2l = _setup()
+    dev = torch.device('cuda:0')
+    model.to(dev)
+    from selfocc_b200.dist import render_sharded
+    planes = [0.5 * torch.randn_like(p) for p in (model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz)]
+    with torch.no_grad():
+        model.head.prepare(representation=planes, metas=metas)
+        a = model.head.render(metas=metas, batch=100)
+        b = render_sharded(model.head, metas, batch=100)
+    assert torch.equal(a['ms_depths'][0], b['ms_depths'][0]) and torch.equal(a['ms_max_depths'][0], b['ms_max_depths'][0])
+    assert torch.equal(a['ms_accs'][0], b['ms_accs'][0])

@@ -59,7 +59,7 @@ def img2lidar_rays(img2lidar, rays, novel_view=None):
         origin[..., 0] += novel_view[0]
         origin[..., 1] += novel_view[1]
         origin[..., 2] += novel_view[2]
-    pad = torch.cat([rays.reshape(1, 1, -1, 2), torch.ones(1, 1, rays.shape[0], 1)], -1)
+    pad = torch.cat([rays.reshape(1, 1, -1, 2), torch.ones(1, 1, rays.shape[0], 1, device=rays.device)], -1)
     direction = torch.matmul(M[..., :3, :3].unsqueeze(2), pad.unsqueeze(-1)).squeeze(-1)
     return origin, direction
 

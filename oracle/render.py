@@ -102,8 +102,8 @@ def aabb_near_far(o, d, aabb, near_plane, training):
     """upstream AABBBoxCollider: slab test with 1/(d + 1e-6); near clamped to near_plane when
     training else 0; far >= near + 1e-6."""
     inv = 1.0 / (d + 1e-6)
-    lo = torch.as_tensor(aabb[:3], dtype=o.dtype)
-    hi = torch.as_tensor(aabb[3:], dtype=o.dtype)
+    lo = torch.as_tensor(aabb[:3], dtype=o.dtype, device=o.device)
+    hi = torch.as_tensor(aabb[3:], dtype=o.dtype, device=o.device)
     t1 = (lo - o) * inv
     t2 = (hi - o) * inv
     nears = torch.minimum(t1, t2).max(-1).values
@@ -117,7 +117,7 @@ def uniform_bins(nears, fars, S, jitter=None):
     """upstream UniformSampler: S bins, edges = near + (far-near)*linspace(0,1,S+1); stratified
     jitter (training, ``perturb=True``) re-draws each edge inside its half-cell given
     ``jitter`` in [0,1) of shape [R, S+1]."""
-    bins = torch.linspace(0.0, 1.0, S + 1, dtype=nears.dtype)[None]
+    bins = torch.linspace(0.0, 1.0, S + 1, dtype=nears.dtype, device=nears.device)[None]
     if jitter is not None:
         ctr = (bins[..., 1:] + bins[..., :-1]) / 2.0
         upper = torch.cat([ctr, bins[..., -1:]], -1)
@@ -154,7 +154,7 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
     prev_cdf = torch.sigmoid(est_prev * inv_s)
     next_cdf = torch.sigmoid(est_next * inv_s)
     alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
-    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=alpha.dtype), 1.0 - alpha + 1e-7], 1), 1)
+    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=alpha.dtype, device=alpha.device), 1.0 - alpha + 1e-7], 1), 1)
     weights = alpha * trans[:, :-1]
     acc = weights.sum(-1)
     # expected-depth renderer incl. its chunk-wide clip, then ray-length -> camera-z units
@@ -171,9 +171,9 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
         rgb_s = torch.relu(raw + 0.5) if sh_act == 'relu' else torch.sigmoid(raw)
         rgb = (weights[..., None] * rgb_s).sum(-2)
         if bkgd == 'white':
-            bg = torch.ones(3)
+            bg = torch.ones(3, device=o.device)
         elif bkgd == 'black':
-            bg = torch.zeros(3)
+            bg = torch.zeros(3, device=o.device)
         elif bkgd == 'random':
             bg = bkgd_rand
         else:
@@ -185,7 +185,7 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
         if h.shape[-1] > 4:
             out['sem'] = (weights[..., None] * torch.softmax(h[..., 4:], -1)).sum(-2)
     else:
-        out['rgb'] = torch.empty(R, 0)  # bev_nerf.py:145-146: no colour channels decoded
+        out['rgb'] = torch.empty(R, 0, device=o.device)  # bev_nerf.py:145-146: no colour channels decoded
     return out
 
 
@@ -198,7 +198,7 @@ def max_depth_ref(weights, ts, deltas):
     return torch.gather(ts, -1, idx).squeeze(-1), idx.squeeze(-1)
 
 
-def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, **kw):
+def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, max_depth_on_cpu=False, **kw):
     """NeuSHead.render (neus_head.py:308-471) after ray generation: origin [1,N,3], direction
     [1,N,R,3] un-normalised.  Serial chunk loop with ``torch.chunk`` sizes when batch > 0."""
     from .rays import flatten_rays, num_chunks
@@ -211,7 +211,11 @@ def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, **kw)
     weights = cat('weights')
     ts = (cat('starts') + cat('ends')) / 2 / nrm
     deltas = (cat('ends') - cat('starts')) / nrm
-    max_depth, max_idx = max_depth_ref(weights, ts, deltas)
+    if max_depth_on_cpu:        # neus_head.py:430-438 moves weights / deltas / ts to the host for this step
+        max_depth, max_idx = max_depth_ref(weights.cpu(), ts.cpu(), deltas.cpu())
+        max_depth, max_idx = max_depth.to(weights.device), max_idx.to(weights.device)
+    else:
+        max_depth, max_idx = max_depth_ref(weights, ts, deltas)
     shp = (bs, n_cam, n_ray)
     return dict(depth=cat('depth').reshape(shp), acc=cat('accumulation').reshape(shp),
                 rgb=cat('rgb').reshape(*shp, -1), vis_normal=cat('normal_vis').reshape(*shp, 3),

@@ -116,7 +116,7 @@ def test_fused_cross_attention_core_matches_rebatch_reference():
     margs, _ = synth.small_mapping(10, 4, rng=30.0)
     mref = GridMeterMappingRef(**margs)
     l2i = _rig(N)
-    tables = ol.ref_3d_tables(mref, [48, 20, 3])      # D = 3 / 20 / 48 exercise the 1- / 2- / 4-way sample split
+    tables = ol.ref_3d_tables(mref, [48, 20, 8])      # D = 8 (vec4, 1 group) / 20 (scalar, 2 groups) / 48 (vec4, 4 groups)
     for r3 in tables:
         D, Q = r3.shape[:2]
         uv_ref, mask_ref = ol.point_sampling_ref(r3[None], l2i[None], (90, 160))

@@ -235,6 +235,14 @@ int so_tpv_cross_attn_forward(const float* value, const int64_t* spatial_shapes,
                               int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t D,
                               void* stream);
 
+/* Strided variants: the value / offsets / logits operands may be column slices of wider row-major matrices (row strides
+ * value_ld / offsets_ld / logits_ld in floats), so ONE projection GEMM can produce the offsets and logits of a query (and
+ * the value tensors of all three planes) side by side without a repacking copy. */
+int so_tpv_cross_attn_forward_strided(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                      const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
+                                      float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q,
+                                      int32_t L, int32_t D, int32_t value_ld, int32_t offsets_ld, int32_t logits_ld, void* stream);
+
 /* A5  visible-query index lists, as the reference builds them with nonzero()
  * (image_cross_attention.py:90-94), without a host sync: for each camera, ascending int64 query
  * indices with any in-frustum point.  index_lists [N, Q] (first lens[cam] entries valid),
@@ -251,6 +259,11 @@ int so_tpv_self_attn_forward(const float* value, const int64_t* spatial_shapes,
                              const float* ref, float* out,
                              int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P,
                              void* stream);
+
+int so_tpv_self_attn_forward_strided(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                     const float* offsets, const float* logits, const float* ref, float* out, int32_t Nv,
+                                     int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P, int32_t value_ld,
+                                     int32_t offsets_ld, int32_t logits_ld, void* stream);
 
 #ifdef __cplusplus
 }

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_cross_attn_kernel(c
                                                              const long long* __restrict__ lsi, const float* __restrict__ offsets,
                                                              const float* __restrict__ logits, const float* __restrict__ uv,
                                                              const unsigned char* __restrict__ vis, float* __restrict__ slots,
-                                                             int* __restrict__ count, int N, int Nv, int Hd, int Q, int L, int D) {
+                                                             int* __restrict__ count, int N, int Nv, int Hd, int Q, int L, int D,
+                                                             int value_ld, int off_ld, int lg_ld) {
   constexpr int LPI = DH / 4;
   constexpr int LANES = LPI * SPLIT;
   __shared__ Levels lv;
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_cross_attn_kernel(c
   if (!live) item = n_items - 1;
   int h = (int)(item % Hd);
   int q = (int)(item / Hd);
-  const int pstride = Hd * DH;
+  const int pstride = value_ld;                       // floats between consecutive pixels of the value tensor
   const int LD = L * D;
-  const float* op = offsets + item * (long long)LD * 2;
-  const float* lg = logits + item * (long long)LD;
+  const float* op = offsets + (long long)q * off_ld + (long long)h * LD * 2;
+  const float* lg = logits + (long long)q * lg_ld + (long long)h * LD;
   float mx, inv_sum;
   softmax_stats<LANES>(lg, LD, li, mx, inv_sum);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_cross_attn_kernel(c
     for (int l = 0; l < L; ++l) {
       const int Hl = lv.h[l], Wl = lv.w[l];
       const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
-      const float* vbase = value + (((long long)cam * Nv + lv.start[l]) * Hd + h) * DH + lc * 4;
+      const float* vbase = value + ((long long)cam * Nv + lv.start[l]) * value_ld + h * DH + lc * 4;
 #pragma unroll 4
       for (int d = sg; d < D; d += SPLIT) {
         float2 r = __ldg(reinterpret_cast<const float2*>(uvp) + d);
@@ -255,7 +256,7 @@ template <int DH>
 __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
                                                             const float* __restrict__ ref, float* __restrict__ out, int Nv, int Hd,
-                                                            int Q, int L, int P) {
+                                                            int Q, int L, int P, int value_ld, int off_ld, int lg_ld) {
   constexpr int LPI = DH / 4;
   __shared__ Levels lv;
   load_levels(lv, shapes, lsi, L);
@@ -267,10 +268,10 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_self_attn_kernel(co
   if (!live) item = n_items - 1;
   int h = (int)(item % Hd);
   int q = (int)(item / Hd);
-  const int pstride = Hd * DH;
+  const int pstride = value_ld;
   const int LP = L * P;
-  const float* op = offsets + item * (long long)LP * 2;
-  const float* lg = logits + item * (long long)LP;
+  const float* op = offsets + (long long)q * off_ld + (long long)h * LP * 2;
+  const float* lg = logits + (long long)q * lg_ld + (long long)h * LP;
   const float* rp = ref + (long long)q * LP * 2;
   float mx, inv_sum;
   softmax_stats<LPI>(lg, LP, lc, mx, inv_sum);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_self_attn_kernel(co
   for (int l = 0; l < L; ++l) {
     const int Hl = lv.h[l], Wl = lv.w[l];
     const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
-    const float* vbase = value + ((long long)lv.start[l] * Hd + h) * DH + lc * 4;
+    const float* vbase = value + (long long)lv.start[l] * value_ld + h * DH + lc * 4;
 #pragma unroll 4
     for (int p = 0; p < P; ++p) {
       float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l * P + p);
@@ -429,21 +430,23 @@ extern "C" int so_point_sampling(const float* ref_3d, const float* lidar2img, in
   return check_launch();
 }
 
-extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                                         const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
-                                         float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q,
-                                         int32_t L, int32_t D, void* stream) {
+extern "C" int so_tpv_cross_attn_forward_strided(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                                 const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
+                                                 float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh,
+                                                 int32_t Q, int32_t L, int32_t D, int32_t value_ld, int32_t offsets_ld,
+                                                 int32_t logits_ld, void* stream) {
   if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !uv || !vis || !slots) return SO_ERR_INVALID_ARG;
   if (N < 1 || Nv < 1 || Hd < 1 || Q < 1 || L < 1 || D < 1) return SO_ERR_INVALID_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (value_ld < Hd * Dh || offsets_ld < Hd * L * D * 2 || logits_ld < Hd * L * D || (value_ld & 3)) return SO_ERR_INVALID_ARG;
   if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
   const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   const int split = D >= 32 ? 4 : (D >= 16 ? 2 : 1);
   long long threads = (long long)Q * Hd * (Dh / 4) * split;
   unsigned grid = (unsigned)ceil_div64(threads, 256);
   ProfScope prof(2, st);
-#define SO_CROSS(DHV, SP) tpv_cross_attn_kernel<DHV, SP><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D)
+#define SO_CROSS(DHV, SP) tpv_cross_attn_kernel<DHV, SP><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D, value_ld, offsets_ld, logits_ld)
   if (Dh == 16) { if (split == 4) SO_CROSS(16, 4); else if (split == 2) SO_CROSS(16, 2); else SO_CROSS(16, 1); }
   else if (Dh == 32) { if (split == 4) SO_CROSS(32, 4); else if (split == 2) SO_CROSS(32, 2); else SO_CROSS(32, 1); }
   else return SO_ERR_UNSUPPORTED;
@@ -452,22 +455,39 @@ extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spat
   return check_launch();
 }
 
-extern "C" int so_tpv_self_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                                        const float* offsets, const float* logits, const float* ref, float* out, int32_t Nv,
-                                        int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P, void* stream) {
+extern "C" int so_tpv_cross_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                         const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
+                                         float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q,
+                                         int32_t L, int32_t D, void* stream) {
+  return so_tpv_cross_attn_forward_strided(value, spatial_shapes, level_start_index, offsets, logits, uv, vis, slots, count, N, Nv,
+                                           Hd, Dh, Q, L, D, Hd * Dh, Hd * L * D * 2, Hd * L * D, stream);
+}
+
+extern "C" int so_tpv_self_attn_forward_strided(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                                const float* offsets, const float* logits, const float* ref, float* out, int32_t Nv,
+                                                int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P, int32_t value_ld,
+                                                int32_t offsets_ld, int32_t logits_ld, void* stream) {
   if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !ref || !out) return SO_ERR_INVALID_ARG;
   if (Nv < 1 || Hd < 1 || Q < 1 || L < 1 || P < 1) return SO_ERR_INVALID_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (value_ld < Hd * Dh || offsets_ld < Hd * L * P * 2 || logits_ld < Hd * L * P || (value_ld & 3)) return SO_ERR_INVALID_ARG;
   if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
   const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
   const long long* lsi = reinterpret_cast<const long long*>(level_start_index);
   long long threads = (long long)Q * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
   ProfScope prof(3, st);
-  SO_DISPATCH_DH(Dh, (tpv_self_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)),
-                 (tpv_self_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P)));
+  SO_DISPATCH_DH(Dh, (tpv_self_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P, value_ld, offsets_ld, logits_ld)),
+                 (tpv_self_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P, value_ld, offsets_ld, logits_ld)));
   note_launch(1);
   return check_launch();
+}
+
+extern "C" int so_tpv_self_attn_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                        const float* offsets, const float* logits, const float* ref, float* out, int32_t Nv,
+                                        int32_t Hd, int32_t Dh, int32_t Q, int32_t L, int32_t P, void* stream) {
+  return so_tpv_self_attn_forward_strided(value, spatial_shapes, level_start_index, offsets, logits, ref, out, Nv, Hd, Dh, Q, L, P,
+                                          Hd * Dh, Hd * L * P * 2, Hd * L * P, stream);
 }
 
 extern "C" int so_visible_index_lists(const uint8_t* mask, int32_t N, int32_t Q, int32_t D, int64_t* index_lists, int32_t* lens,

@@ -156,6 +156,30 @@ def fast_linear(lin, x, relu=False, residual=None):
     return out if residual is None else out + residual
 
 
+def fast_linear_cat(owner, key, lins, x):
+    """Several nn.Linear layers applied to the SAME input as one tcgen05 GEMM (weights concatenated along N, cached on
+    ``owner``).  Returns the [M, sum(N_i)] result and the column slices (views, unit column stride) of each layer."""
+    ver = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version, l.bias.data_ptr()) for l in lins)
+    ent = getattr(owner, key, None)
+    if ent is None or ent[0] != ver:
+        with torch.no_grad():
+            w = torch.cat([l.weight.detach() for l in lins], 0).contiguous()
+            b = torch.cat([l.bias.detach() for l in lins], 0).contiguous()
+            hi, lo = ops.split_tf32(w)
+        ent = (ver, hi, lo, b, [l.weight.shape[0] for l in lins])
+        setattr(owner, key, ent)
+    y = ops.linear_3xtf32(x.contiguous(), ent[1], ent[2], ent[3])
+    outs, c0 = [], 0
+    for n in ent[4]:
+        outs.append(y[:, c0:c0 + n])
+        c0 += n
+    return y, outs
+
+
+def _fusable(lins, x):
+    return x.is_cuda and x.dtype == torch.float32 and all(ops.linear_supported(l.weight.shape[1]) for l in lins)
+
+
 def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -196,11 +220,17 @@ class CrossViewHybridAttention(_DeformBase):
             raise ValueError('Last dim of reference_points must be 2, but get %d instead.' % reference_points.shape[-1])
         fused = bs == 1 and key_padding_mask is None and not _needs_grad(value, query, self.value_proj.weight)
         if fused:   # inference: tensor-core projections + one fused sampling kernel, dropout is the identity
-            v = fast_linear(self.value_proj, value[0]).view(num_value, Hd, -1)
-            offsets = fast_linear(self.sampling_offsets, query[0]).view(num_query, Hd, L, P, 2)
-            logits = fast_linear(self.attention_weights, query[0]).view(num_query, Hd, L, P)
+            v = fast_linear(self.value_proj, value[0])
             ref = reference_points[0] if reference_points.dim() == 5 else reference_points
-            out = ops.tpv_self_attn_forward(v, spatial_shapes, level_start_index, offsets, logits, ref.contiguous())
+            if _fusable([self.sampling_offsets, self.attention_weights], query):
+                _, (offsets, logits) = fast_linear_cat(self, '_so_offlog', [self.sampling_offsets, self.attention_weights], query[0])
+                out = ops.tpv_self_attn_forward_rows(v, Hd, v.shape[1] // Hd, spatial_shapes, level_start_index, offsets, logits,
+                                                     ref.contiguous(), L, P)
+            else:
+                offsets = fast_linear(self.sampling_offsets, query[0]).view(num_query, Hd, L, P, 2)
+                logits = fast_linear(self.attention_weights, query[0]).view(num_query, Hd, L, P)
+                out = ops.tpv_self_attn_forward(v.view(num_value, Hd, -1), spatial_shapes, level_start_index, offsets, logits,
+                                                ref.contiguous())
             idt = identity[0] if self.batch_first else identity[:, 0]
             if self.training:
                 out = self.dropout(fast_linear(self.output_proj, out)) + idt
@@ -285,9 +315,11 @@ class BEVCrossAttention(nn.Module):
         nn.init.constant_(self.output_proj.bias, 0.)
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None,
-                bev_masks=None, level_start_index=None, bev_vis=None, **kwargs):
+                bev_masks=None, level_start_index=None, bev_vis=None, value_rows=None, **kwargs):
         """query [B,Q,C]; key/value [N, sum(hw), B, C]; reference_points_cams [N,B,Q,D,2];
-        bev_masks [N,B,Q,D] (bool/uint8); bev_vis optional uint8 [N,Q] = any_D(mask) from so_point_sampling."""
+        bev_masks [N,B,Q,D] (bool/uint8); bev_vis optional uint8 [N,Q] = any_D(mask) from so_point_sampling;
+        value_rows optional [N*sum(hw), >= C] view holding value_proj(value) already (TPVCrossAttention projects the image
+        features for its three planes in one GEMM)."""
         if key is None:
             key = query
         if value is None:
@@ -300,13 +332,19 @@ class BEVCrossAttention(nn.Module):
         assert reference_points_cams.size(3) == D
         if bs == 1 and not _needs_grad(query, value, da.value_proj.weight):
             n_cam, nv = value.shape[0], value.shape[1]
-            v = fast_linear(da.value_proj, value[:, :, 0]).view(n_cam, nv, Hd, -1)
-            offsets = fast_linear(da.sampling_offsets, query[0]).view(num_query, Hd, L, D, 2)
-            logits = fast_linear(da.attention_weights, query[0]).view(num_query, Hd, L, D)
             if bev_vis is None:
                 bev_vis = (bev_masks[:, 0].sum(-1) > 0).to(torch.uint8)
-            slots = ops.tpv_cross_attn_forward(v, spatial_shapes, level_start_index, offsets, logits,
-                                               reference_points_cams[:, 0].contiguous(), bev_vis.contiguous())
+            uv = reference_points_cams[:, 0].contiguous()
+            v_rows = value_rows if value_rows is not None else fast_linear(da.value_proj, value[:, :, 0]).view(n_cam * nv, -1)
+            if _fusable([da.sampling_offsets, da.attention_weights], query):
+                _, (offsets, logits) = fast_linear_cat(da, '_so_offlog', [da.sampling_offsets, da.attention_weights], query[0])
+                slots = ops.tpv_cross_attn_forward_rows(v_rows, n_cam, Hd, C // Hd, spatial_shapes, level_start_index, offsets, logits,
+                                                        uv, bev_vis.contiguous(), L, D)
+            else:
+                offsets = fast_linear(da.sampling_offsets, query[0]).view(num_query, Hd, L, D, 2)
+                logits = fast_linear(da.attention_weights, query[0]).view(num_query, Hd, L, D)
+                slots = ops.tpv_cross_attn_forward(v_rows.contiguous().view(n_cam, nv, Hd, -1), spatial_shapes, level_start_index,
+                                                   offsets, logits, uv, bev_vis.contiguous())
             if self.training:
                 return self.dropout(fast_linear(self.output_proj, slots))[None] + residual
             return fast_linear(self.output_proj, slots, residual=residual[0])[None]
@@ -359,10 +397,15 @@ class TPVCrossAttention(nn.Module):
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None, tpv_masks=None,
                 level_start_index=None, tpv_vis=None, **kwargs):
+        rows = [None, None, None]
+        vps = [a.deformable_attention.value_proj for a in self.attns]
+        if value.shape[2] == 1 and _fusable(vps, value) and not _needs_grad(value, query[0], vps[0].weight):
+            # the three planes project the SAME image features with their own value_proj: one GEMM, three column slices
+            _, rows = fast_linear_cat(self, '_so_value3', vps, value[:, :, 0].reshape(-1, value.shape[-1]))
         return [self.attns[i](query[i], key, value, residual[i] if residual is not None else None,
                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                               reference_points_cams=reference_points_cams[i], bev_masks=tpv_masks[i],
-                              bev_vis=None if tpv_vis is None else tpv_vis[i]) for i in range(3)]
+                              bev_vis=None if tpv_vis is None else tpv_vis[i], value_rows=rows[i]) for i in range(3)]
 
 
 class FFN(nn.Module):

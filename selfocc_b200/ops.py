@@ -401,3 +401,37 @@ def layer_norm(x, gamma, beta, eps=1e-5, add=None):
     _lib.check(lib.so_layer_norm(_p(x), _p(add), _p(gamma), _p(beta), _p(y), x.numel() // Cn, Cn, float(eps), _stream()),
                'so_layer_norm')
     return y
+
+
+def _rows(t, name):
+    """2-D row-major view whose rows may be a column slice of a wider matrix: returns (tensor, row stride in floats)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError('%s must be a CUDA fp32 tensor: selfocc_b200 has no CPU fallback' % name)
+    assert t.dim() == 2 and t.stride(1) == 1, '%s must be a [rows, cols] view with unit column stride' % name
+    return t, t.stride(0)
+
+
+def tpv_cross_attn_forward_rows(value_rows, n_cam, Hd, Dh, spatial_shapes, level_start_index, offsets_rows, logits_rows, uv, vis, L, D):
+    """Strided form: value_rows [n_cam*Nv, >= Hd*Dh] view, offsets_rows [Q, Hd*L*D*2] view, logits_rows [Q, Hd*L*D] view."""
+    lib = _lib.load()
+    v, vld = _rows(value_rows, 'value'); o, old = _rows(offsets_rows, 'offsets'); lg, lld = _rows(logits_rows, 'logits')
+    _chk(uv, name='uv'); _chk(vis, torch.uint8, 'vis')
+    Q = o.shape[0]
+    Nv = v.shape[0] // n_cam
+    slots = torch.empty(Q, Hd * Dh, device=v.device)
+    _lib.check(lib.so_tpv_cross_attn_forward_strided(_p(v), _p(spatial_shapes), _p(level_start_index), _p(o), _p(lg), _p(uv), _p(vis),
+                                                     _p(slots), _p(None), n_cam, Nv, Hd, Dh, Q, L, D, vld, old, lld, _stream()),
+               'so_tpv_cross_attn_forward_strided')
+    return slots
+
+
+def tpv_self_attn_forward_rows(value_rows, Hd, Dh, spatial_shapes, level_start_index, offsets_rows, logits_rows, ref, L, P):
+    lib = _lib.load()
+    v, vld = _rows(value_rows, 'value'); o, old = _rows(offsets_rows, 'offsets'); lg, lld = _rows(logits_rows, 'logits')
+    _chk(ref, name='ref')
+    Q = o.shape[0]
+    out = torch.empty(Q, Hd * Dh, device=v.device)
+    _lib.check(lib.so_tpv_self_attn_forward_strided(_p(v), _p(spatial_shapes), _p(level_start_index), _p(o), _p(lg), _p(ref), _p(out),
+                                                    v.shape[0], Hd, Dh, Q, L, P, vld, old, lld, _stream()),
+               'so_tpv_self_attn_forward_strided')
+    return out

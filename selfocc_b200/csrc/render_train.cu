@@ -119,7 +119,9 @@ __device__ __forceinline__ void sample_colour(const VolumeDev& V, const RenderDe
   }
 }
 
-template <bool HAS_RGB, bool HAS_SEM>
+// FAST = affine metre->grid map, S a power of two (multiple of 32), cos-anneal finished, mid-point anchor: lean per-sample
+// path (closed-form jittered edges, interior gather chosen by a warp vote, base-2 alpha), ~2.4x fewer instructions.
+template <bool HAS_RGB, bool HAS_SEM, bool FAST>
 __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                                const float* __restrict__ bkgd_rand, TrainOut O) {
   const int lane = threadIdx.x & 31;
@@ -139,11 +141,44 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
     float sem_acc[HAS_SEM ? kMaxSem : 1];
     if (HAS_SEM)
       for (int c = 0; c < kMaxSem; ++c) sem_acc[c] = 0.f;
+    const float step = 1.0f / (float)S, span = c.tf - c.tn, k_log2 = P.inv_s * 1.4426950408889634f;
     for (int k = 0; k < K; ++k) {
       int s = k * 32 + lane;
       bool live = s < S;
       Sample q;
-      eval_sample(V, P, c, live ? s : S - 1, lane, q);
+      if (FAST) {
+        // edge i is re-drawn inside [max(i - 1/2, 0), min(i + 1/2, S)] / S (exact arithmetic for power-of-two S)
+        auto edge = [&](int i) {
+          float fi = (float)i;
+          float lo_b = fmaxf(fi - 0.5f, 0.f) * step, up_b = fminf(fi + 0.5f, (float)S) * step;
+          float b = c.u ? fmaf(up_b - lo_b, __ldg(c.u + i), lo_b) : fi * step;
+          return fmaf(b, span, c.tn);
+        };
+        float e0 = edge(s);
+        float e_next = edge(k * 32 + 32);                 // warp-uniform: right edge of lane 31
+        float e1 = __shfl_down_sync(0xffffffffu, e0, 1);
+        if (lane == 31) e1 = e_next;
+        q.mid = 0.5f * (e0 + e1);
+        q.delta = e1 - e0;
+        float gh = fmaf(c.gdh, q.mid, c.gh0), gw = fmaf(c.gdw, q.mid, c.gw0), gd = fmaf(c.gdd, q.mid, c.gd0);
+        q.kh = V.ax[0].k0; q.kw = V.ax[1].k0; q.kd = V.ax[2].k0;
+        float flh = floorf(gh), flw = floorf(gw), flz = floorf(gd);
+        int h0 = (int)flh, w0 = (int)flw, z0 = (int)flz;
+        bool interior = (unsigned)h0 < (unsigned)(V.H - 1) && (unsigned)w0 < (unsigned)(V.W - 1) && (unsigned)z0 < (unsigned)(V.Z - 1);
+        float dgh, dgw, dgd;
+        if (__all_sync(0xffffffffu, interior)) {
+          gather_sdf_interior(V, h0, w0, z0, gh - flh, gw - flw, gd - flz, q.sdf, dgh, dgw, dgd);
+          if (HAS_RGB) q.t = make_taps(V, gh, gw, gd);
+        } else {
+          q.t = make_taps(V, gh, gw, gd);
+          gather_sdf(V, q.t, q.sdf, dgh, dgw, dgd);
+        }
+        q.gx = dgw * q.kw; q.gy = dgh * q.kh; q.gz = dgd * q.kd;
+        float tc = c.d[0] * q.gx + c.d[1] * q.gy + c.d[2] * q.gz;
+        q.alpha = neus_alpha_log2(q.sdf * k_log2, fminf(tc, 0.f) * (q.delta * (0.5f * k_log2)));
+      } else {
+        eval_sample(V, P, c, live ? s : S - 1, lane, q);
+      }
       float alpha = live ? q.alpha : 0.f;
       float f = live ? (1.0f - alpha + 1e-7f) : 1.0f;
       float incl = warp_incl_prod(f, lane);
@@ -431,9 +466,13 @@ extern "C" int so_render_train_forward(const float* vol_sdf, const float* vol_fe
   long long ctas = ceil_div64(R.ray_count, 4);
   unsigned grid = (unsigned)(ctas < (long long)kNumSMs * 16 ? ctas : (long long)kNumSMs * 16);
   ProfScope prof(6, st);
-  if (want_sem) render_train_fwd_kernel<true, true><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O);
-  else if (want_rgb) render_train_fwd_kernel<true, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O);
-  else render_train_fwd_kernel<false, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O);
+  const bool fast = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f && (P.S & (P.S - 1)) == 0 && P.S >= 32 &&
+                    P.cos_anneal == 1.0f && P.anchor_mid;
+#define SO_TRAIN_FWD(RGB, SEM, F) render_train_fwd_kernel<RGB, SEM, F><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O)
+  if (want_sem) { if (fast) SO_TRAIN_FWD(true, true, true); else SO_TRAIN_FWD(true, true, false); }
+  else if (want_rgb) { if (fast) SO_TRAIN_FWD(true, false, true); else SO_TRAIN_FWD(true, false, false); }
+  else { if (fast) SO_TRAIN_FWD(false, false, true); else SO_TRAIN_FWD(false, false, false); }
+#undef SO_TRAIN_FWD
   note_launch(1);
   return check_launch();
 }

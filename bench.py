@@ -138,7 +138,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))   # a lost rank must fail, not hang
     assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node == --gpus'
     _lib.load()
     model, cfg = build_model(args.workload, dev)
@@ -165,11 +166,12 @@ def run_b200(args):
         packed = torch.stack([out['ms_depths'][0].reshape(-1), out['ms_max_depths'][0].reshape(-1)], -1)
         return all_gather_rays(packed, world * rays_per_frame)     # the one collective (frames are equal-sized slices)
 
-    def timed(fn, K, W, sampler=None):
+    def timed(fn, K, W, sampler=None, sample_clocks=False):
         if sampler:
             sampler.start()                                        # nvidia-smi needs ~100s of ms to start: sample from warm-up on
-            for _ in range(20):                                    # extra untimed steps so the clocks are sampled under load
-                fn()
+        if sample_clocks:
+            for _ in range(20):                                    # extra untimed steps (ALL ranks: fn may hold a collective)
+                fn()                                               # so that the clocks are sampled under load
         for _ in range(W):
             flush.zero_()
             fn()
@@ -201,7 +203,7 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     _lib.profile_enable(True)
     sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler)
+    total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler, sample_clocks=True)
     prof = _lib.profile_read()
     ms_per_step = total_ms / K
     value = world * rays_per_frame / (ms_per_step * 1e-3)

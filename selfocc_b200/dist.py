@@ -53,3 +53,24 @@ def render_sharded(head, metas, batch=0, group=None):
     for i, k in enumerate(keys):
         res[k] = [full[:, i].reshape(1, n_cam, sampler.ray_number)]
     return res
+
+
+def uniform_sdf_sharded(head, aabb, resolution, group=None):
+    """Occupancy lattice of NeuSHead.forward_occ / get_uniform_sdf (neus_head.py:265-293) with the lattice points
+    sharded over the process group (BASELINE configs[3]): each rank queries a contiguous slice of the
+    flattened [H, W, D] lattice and ONE all_gather assembles the sdf.  ``head.prepare()`` must have run on every rank."""
+    from . import ops
+    f = head.model.field
+    dev = f.vol_sdf.device
+    xs = torch.linspace(aabb[0], aabb[3], int((aabb[3] - aabb[0]) / resolution), device=dev)
+    ys = torch.linspace(aabb[1], aabb[4], int((aabb[4] - aabb[1]) / resolution), device=dev)
+    zs = torch.linspace(aabb[2], aabb[5], int((aabb[5] - aabb[2]) / resolution), device=dev)
+    W, H, D = len(xs), len(ys), len(zs)
+    xyz = torch.stack([xs[None, :, None].expand(H, W, D), ys[:, None, None].expand(H, W, D),
+                       zs[None, None, :].expand(H, W, D)], dim=-1).flatten(0, 2)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    total = xyz.shape[0]
+    begin, count = ray_slice(total, world, rank)
+    local = ops.field_query(f.vol_sdf, f.vol_feat, f.desc, xyz[begin:begin + count].contiguous())[0]
+    return all_gather_rays(local, total, group).reshape(H, W, D), xyz.reshape(H, W, D, 3)

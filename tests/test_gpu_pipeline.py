@@ -164,3 +164,43 @@ def test_render_sharded_single_process_equals_render():
         b = render_sharded(model.head, metas, batch=100)
     assert torch.equal(a['ms_depths'][0], b['ms_depths'][0]) and torch.equal(a['ms_max_depths'][0], b['ms_max_depths'][0])
     assert torch.equal(a['ms_accs'][0], b['ms_accs'][0])
+
+
+def test_kitti_like_mono_config_with_half_axis_and_colour():
+    """BASELINE configs[3] shape class (config/kitti/kitti_occ.py:166-176,188,322): ONE camera, h axis not mirrored
+    (h_half=True), colour decoded (color_dims=3), Z with a padded pitch; render + occupancy lattice vs the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender, rays as orays
+    from selfocc_b200.dist import uniform_sdf_sharded
+    torch.manual_seed(1)
+    dev = torch.device('cuda:0')
+    margs = dict(nonlinear_mode='linear', h_size=[16, 0], h_range=[25.6, 0], h_half=True, w_size=[8, 0], w_range=[12.8, 0],
+                 w_half=False, d_size=[8, 0], d_range=[-2.0, 4.4, 4.4])
+    rng = [-12.8, 0.0, -2.0, 12.8, 25.6, 4.4]
+    cfg = configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=1, num_layers=1, num_points_cross=(6, 6, 4),
+                                  num_points_self=4, num_samples=64, ray_number=(11, 38), ray_img_size=(88, 304), color_dims=3)
+    model = build_head(cfg).eval().to(dev)
+    l2i, i2l = synth.camera_rig((0.,), f=180., cx=152., cy=44., height=0.3, radius=0.1)
+    metas = [dict(lidar2img=list(l2i), img2lidar=list(i2l), img_shape=(88, 304))]
+    feats = [torch.randn(1, 1, 96, h, w, device=dev) for h, w in [(11, 38), (6, 19), (3, 10), (2, 5)]]
+    with torch.no_grad():
+        res = model(ms_img_feats=feats, metas=metas, prepare=True)
+        out = model.head.render(metas=metas, batch=200)
+        sdf_grid, xyz = uniform_sdf_sharded(model.head, rng, 0.8)
+    mref = GridMeterMappingRef(**margs)
+    f = model.head.model.field
+    w1, b1, w2, b2 = (t.detach().cpu().double() for t in (f.density_net[1].weight, f.density_net[1].bias,
+                                                         f.density_net[3].weight, f.density_net[3].bias))
+    planes = [p.detach().cpu().double() for p in res['representation']]
+    vol = orender.tpv_decode_ref(planes[0][0], planes[1][0], planes[2][0], (mref.size_h, mref.size_w, mref.size_d), w1, b1, w2, b2)
+    origin, direction = orays.img2lidar_rays(torch.tensor(i2l, dtype=torch.float32)[None], orays.fixed_ray_grid([11, 38], [88, 304]))
+    ref = orender.head_render_ref(vol, mref, origin.double(), direction.double(), rng, float(f.deviation_network.get_variance()),
+                                  batch=200, S=64, color_dims=3, bkgd='white')
+    d, dref = out['ms_depths'][0].cpu(), ref['depth'].float()
+    assert d.shape == (1, 1, 418)
+    assert ((d - dref).abs() / dref.abs().clamp_min(1e-6)).max().item() < 1e-4
+    assert torch.allclose(out['ms_colors'][0].cpu(), ref['rgb'].float(), atol=5e-5)
+    sdf_ref, _, xyz_ref = orender.uniform_sdf_ref(vol, mref, rng, 0.8)
+    assert torch.allclose(xyz.cpu(), xyz_ref, atol=1e-5) and torch.allclose(sdf_grid.cpu(), sdf_ref.float(), atol=3e-5)

@@ -81,3 +81,21 @@ def test_ray_sampler_grid_equals_table(golden):
     np.random.seed(123)
     rc = RaySampler('cellular', [6, 10], [90, 160], ray_upper_crop=8)
     assert torch.allclose(rc(), torch.from_numpy(golden['rays_cell_6x10_90x160']), atol=1e-5)
+
+
+def test_product_mapping_matches_reference_golden(golden):
+    """The product-side GridMeterMapping (construction-time tables, C-ABI axis table) against the reference's own outputs,
+    including half axes and outer rings."""
+    from selfocc_b200.mapping import GridMeterMapping
+    T = lambda a: torch.from_numpy(golden[a])
+    ring = GridMeterMapping(nonlinear_mode='linear', h_size=[8, 4], h_range=[10., 20.], h_half=True, w_size=[6, 2],
+                            w_range=[12., 8.], w_half=False, d_size=[4, 2], d_range=[-2.0, 2.0, 6.0])
+    assert (ring.size_h, ring.size_w, ring.size_d) == (13, 17, 7)
+    assert torch.equal(ring.meter2grid(T('map_ring_meter'), True), T('map_ring_m2g'))
+    assert torch.equal(ring.grid2meter(T('map_ring_grid')), T('map_ring_g2m'))
+    nus = GridMeterMapping(**synth.NUSC_MAPPING)
+    assert torch.equal(nus.meter2grid(T('map_nus_meter')), T('map_nus_m2g'))
+    assert torch.equal(nus.grid2meter(T('map_nus_grid')), T('map_nus_g2m'))
+    d = ring.volume_desc(3)
+    assert (d.H, d.W, d.Z, d.zpitch, d.n_feat, d.feat_pitch) == (13, 17, 7, 8, 3, 4)
+    assert d.axis[0].offset == 0.0 and d.axis[1].offset == 8.0 and d.axis[2].start == -2.0 and d.axis[2].size1 == 2.0

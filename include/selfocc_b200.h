@@ -85,6 +85,9 @@ int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz,
                   const float* w1, const float* b1, const float* w2, const float* b2,
                   const so_volume_desc* vol_host, float* vol_sdf, float* vol_feat, void* stream);
 
+/* Test hook: force the fp32 SIMT decode kernel (default: the tcgen05 3xTF32 kernel whenever C % 32 == 0). */
+int so_tpv_decode_force_simt(int on);
+
 /* ---------------------------------------------------------------------------------------
  * Ray set of one frame: n_cam cameras x rays_per_cam pixel rays, flattened (cam, ray)-major
  * exactly like neus_head.py:324-325.  Pixel coordinates come either from `pix` ([rays_per_cam, 2]

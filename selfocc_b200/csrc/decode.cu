@@ -8,7 +8,7 @@
 // is the 30 MB of planes (L2-resident across CTAs) and the decoded volume itself.
 // fp32 SIMT on purpose: the decoded sdf feeds a 1e-4-relative depth parity bar (fp32 reference,
 // autocast disabled at bev_nerf.py:73).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace so {
 
@@ -121,6 +121,211 @@ __global__ void __launch_bounds__(kThreads) tpv_decode_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core variant (tcgen05, same 3xTF32 operand splitting as gemm.cu so the decoded sdf keeps fp32-level accuracy).
+// Persistent CTA per SM, 14 warps:
+//   warps 0-7  builders   A tile = softplus(hw + zh + wz) for 128 voxels x 32 channels at a time, split into TF32 hi / lo and
+//                         written straight into the 128B-swizzled K-major UMMA layout (no TMA: the operand is computed)
+//   warp  8    MMA        12 x tcgen05.mma.kind::tf32 per atom (hi*hi, lo*hi, hi*lo) into a double-buffered TMEM accumulator
+//   warps 10-13 epilogue   tcgen05.ld -> +b1 -> softplus -> second Linear (1 + n_feat outputs, register dot products) -> volume
+// W1 (hi and lo, swizzled) stays resident in shared memory for the whole kernel.
+constexpr int kDecThreads = 448;
+constexpr int kDecBuilders = 256;
+constexpr int kDecStagesMax = 4;
+
+struct DecSmem {
+  int atoms, stages, w_bytes, ring, w2, b1, b2, bars, total;
+};
+__host__ __device__ inline DecSmem dec_smem(int C, int n_out) {
+  DecSmem m;
+  m.atoms = C / kAtomK;
+  m.w_bytes = 2 * m.atoms * C * 128;                          // W1 hi + lo: atoms x [C rows x 128 B]
+  const int fixed = m.w_bytes + n_out * C * 4 + C * 4 + 128 + 256;
+  int st = (227 * 1024 - 1024 - fixed) / (2 * kAtomBytesA);
+  m.stages = st > kDecStagesMax ? kDecStagesMax : st;
+  m.ring = m.w_bytes;
+  m.w2 = m.ring + m.stages * 2 * kAtomBytesA;
+  m.b1 = m.w2 + n_out * C * 4;
+  m.b2 = m.b1 + C * 4;
+  m.bars = m.b2 + 128;
+  m.total = m.bars + 256 + 1024;
+  return m;
+}
+
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// NOUT = compile-time upper bound of the second layer's width (1 + n_feat): the per-row outputs stay in registers
+template <int NOUT>
+__global__ void __launch_bounds__(kDecThreads, 1)
+tpv_decode_tc_kernel(const float* __restrict__ hw, const float* __restrict__ zh, const float* __restrict__ wz,
+                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                     const float* __restrict__ b2, int C, int H, int W, int Z, int zpitch, int n_out, int feat_pitch,
+                     float* __restrict__ vol_sdf, float* __restrict__ vol_feat, int tiles_per_row, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const DecSmem L = dec_smem(C, n_out);
+  const int KA = L.atoms, stages = L.stages;
+  uint8_t* w_hi = sm;
+  uint8_t* w_lo = sm + KA * C * 128;
+  uint8_t* ring = sm + L.ring;
+  float* W2s = reinterpret_cast<float*>(sm + L.w2);
+  float* b1s = reinterpret_cast<float*>(sm + L.b1);
+  float* b2s = reinterpret_cast<float*>(sm + L.b2);
+  uint64_t* conv = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* empty = conv + kDecStagesMax;
+  uint64_t* tmem_full = empty + kDecStagesMax;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int WZ = W * Z;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDecStagesMax; ++s) { mbar_init(conv + s, kDecBuilders); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 256);
+  // W1 [out j][in k] is K-major already: split it and lay it out as KA swizzled atoms of [C rows x 32 k]
+  for (int i = tid; i < C * C / 4; i += kDecThreads) {
+    int j = (i * 4) / C, k = (i * 4) % C;
+    float4 v = __ldg(reinterpret_cast<const float4*>(w1) + i), h, l;
+    h.x = tf32_rn(v.x); l.x = v.x - h.x; h.y = tf32_rn(v.y); l.y = v.y - h.y;
+    h.z = tf32_rn(v.z); l.z = v.z - h.z; h.w = tf32_rn(v.w); l.w = v.w - h.w;
+    uint32_t off = (uint32_t)((k / kAtomK) * C * 128) + swz_off(j, (k % kAtomK) / 4);
+    *reinterpret_cast<float4*>(w_hi + off) = h;
+    *reinterpret_cast<float4*>(w_lo + off) = l;
+  }
+  for (int i = tid; i < n_out * C; i += kDecThreads) W2s[i] = __ldg(w2 + i);
+  for (int i = tid; i < C; i += kDecThreads) b1s[i] = __ldg(b1 + i);
+  for (int i = tid; i < n_out; i += kDecThreads) b2s[i] = __ldg(b2 + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===== builders: thread owns 16-byte chunk c4 of rows r = tid/8 + 32 j =====
+    const int c4 = tid & 7, r0 = tid >> 3;
+    const float inv_z = 1.0f / (float)Z;
+    int s = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int h = t / tiles_per_row, v0 = (t - h * tiles_per_row) * kBM;
+      // (w, z) of this thread's four voxel rows; (v + 1/2) / Z is at least 1/(2Z) away from an integer, so the float
+      // floor is exact
+      int vv[4], ww[4], zz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        vv[j] = v0 + r0 + 32 * j;
+        ww[j] = __float2int_rd(((float)vv[j] + 0.5f) * inv_z);
+        zz[j] = vv[j] - ww[j] * Z;
+      }
+      for (int a = 0; a < KA; ++a) {
+        mbar_wait(empty + s, ph ^ 1);
+        uint8_t* hi = ring + s * 2 * kAtomBytesA;
+        uint8_t* lo = hi + kAtomBytesA;
+        const int kc = a * kAtomK + c4 * 4;
+        float4 x[4], y[4], u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // all 12 loads of the atom in flight before any use
+          const bool ok = vv[j] < WZ;
+          x[j] = ok ? __ldg(reinterpret_cast<const float4*>(hw + ((size_t)h * W + ww[j]) * C + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          y[j] = ok ? __ldg(reinterpret_cast<const float4*>(zh + ((size_t)zz[j] * H + h) * C + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u[j] = ok ? __ldg(reinterpret_cast<const float4*>(wz + (size_t)vv[j] * C + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (vv[j] < WZ) {
+            f.x = softplus_fast(x[j].x + y[j].x + u[j].x); f.y = softplus_fast(x[j].y + y[j].y + u[j].y);
+            f.z = softplus_fast(x[j].z + y[j].z + u[j].z); f.w = softplus_fast(x[j].w + y[j].w + u[j].w);
+          }
+          float4 hh, ll;
+          hh.x = tf32_rn(f.x); ll.x = f.x - hh.x; hh.y = tf32_rn(f.y); ll.y = f.y - hh.y;
+          hh.z = tf32_rn(f.z); ll.z = f.z - hh.z; hh.w = tf32_rn(f.w); ll.w = f.w - hh.w;
+          const uint32_t off = swz_off(r0 + 32 * j, c4);
+          *reinterpret_cast<float4*>(hi + off) = hh;
+          *reinterpret_cast<float4*>(lo + off) = ll;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(conv + s);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(C);
+      const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(tmem_empty + acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        uint32_t accum = 0;
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait(conv + s, ph);
+          tc_fence_after();
+          const uint32_t ahi = smem_u32(ring + s * 2 * kAtomBytesA), alo = ahi + kAtomBytesA;
+          const uint32_t bhi = whi + a * C * 128, blo = wlo + a * C * 128;
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t ab = prod == 1 ? alo : ahi;
+            const uint32_t bb = prod == 2 ? blo : bhi;
+#pragma unroll
+            for (int k = 0; k < kAtomK / 8; ++k) {
+              umma_tf32(d_tmem, make_desc(ab + k * 32), make_desc(bb + k * 32), idesc, accum);
+              accum = 1u;
+            }
+          }
+          umma_commit(empty + s);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tmem_full + acc);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 10) {
+    // ===== epilogue: hidden = softplus(acc + b1); out = W2 hidden + b2 =====
+    const int q = warp & 3;                               // warps 10..13 -> TMEM lane quarters 2,3,0,1
+    const int r = q * 32 + lane;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int h = t / tiles_per_row, v = (t - h * tiles_per_row) * kBM + r;
+      mbar_wait(tmem_full + acc, acc_ph);
+      tc_fence_after();
+      float out[NOUT];
+#pragma unroll
+      for (int c = 0; c < NOUT; ++c) out[c] = c < n_out ? b2s[c] : 0.f;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t rg[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), rg);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float hdn = softplus_fast(__uint_as_float(rg[j]) + b1s[c0 + j]);
+#pragma unroll
+          for (int c = 0; c < NOUT; ++c)
+            if (c < n_out) out[c] = fmaf(hdn, W2s[c * C + c0 + j], out[c]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (v < WZ) {
+        const int w = v / Z, z = v - w * Z;
+        vol_sdf[((size_t)h * W + w) * zpitch + z] = out[0];
+#pragma unroll
+        for (int c = 1; c < NOUT; ++c)
+          if (c < n_out) vol_feat[(((size_t)h * W + w) * Z + z) * feat_pitch + (c - 1)] = out[c];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
+}
+
 __global__ void zero_pad_kernel(float* vol_sdf, long long columns, int Z, int zpitch) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int pad = zpitch - Z;
@@ -153,6 +358,10 @@ int launch_decode(const float* hw, const float* zh, const float* wz, const float
 
 using namespace so;
 
+static bool g_decode_force_simt = false;
+// Test hook: 1 = use the fp32 SIMT decode kernel even where the tcgen05 kernel applies (both are parity-tested).
+extern "C" int so_tpv_decode_force_simt(int on) { g_decode_force_simt = on != 0; return SO_OK; }
+
 extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C, const float* w1,
                              const float* b1, const float* w2, const float* b2, const so_volume_desc* d,
                              float* vol_sdf, float* vol_feat, void* stream) {
@@ -167,6 +376,29 @@ extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const flo
     long long n = (long long)d->H * d->W * (d->zpitch - d->Z);
     zero_pad_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(vol_sdf, (long long)d->H * d->W, d->Z, d->zpitch);
     note_launch(1);
+  }
+  if (C % 32 == 0 && C >= 32 && C <= 128 && !g_decode_force_simt) {
+    const int n_out = 1 + d->n_feat;
+    DecSmem Ls = dec_smem(C, n_out);
+    if (Ls.stages >= 2) {
+      static bool attr_tc = false;
+      if (!attr_tc) {
+        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
+        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
+        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
+        attr_tc = true;
+      }
+      const int tiles_per_row = (int)ceil_div64((int64_t)d->W * d->Z, kBM);
+      const int n_tiles = tiles_per_row * d->H;
+      const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+      ProfScope prof(1, st);
+#define SO_DEC_TC(NO) tpv_decode_tc_kernel<NO><<<grid, kDecThreads, Ls.total, st>>>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, C, d->H, d->W, d->Z, \
+                                                                                  d->zpitch, n_out, d->feat_pitch, vol_sdf, vol_feat, tiles_per_row, n_tiles)
+      if (n_out == 1) SO_DEC_TC(1); else if (n_out <= 4) SO_DEC_TC(4); else SO_DEC_TC(32);
+#undef SO_DEC_TC
+      note_launch(1);
+      return check_launch();
+    }
   }
   switch (C) {
     case 32: return launch_decode<32>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, st);

@@ -29,33 +29,37 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines: build an experimental variant (e.g. out='libexp.so', defines=['-DSO_RENDER_UNROLL=4']) next to the
+    default library; select it at run time with SELFOCC_B200_LIB=<path>."""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
+    tag = '' if out is None else '.' + os.path.splitext(os.path.basename(out))[0]
     objs = []
     procs = []
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     for s in srcs:
-        o = os.path.join(LIB_DIR, s.replace('.cu', '.o'))
+        o = os.path.join(LIB_DIR, s.replace('.cu', tag + '.o'))
         objs.append(o)
-        cmd = [_nvcc()] + NVCC_FLAGS + PER_SOURCE_FLAGS.get(s, []) + ['-c', os.path.join(CSRC, s), '-o', o]
+        cmd = [_nvcc()] + NVCC_FLAGS + PER_SOURCE_FLAGS.get(s, []) + list(defines) + ['-c', os.path.join(CSRC, s), '-o', o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:
-        out, _ = p.communicate()
-        log.append('== %s\n%s' % (s, out))
+        text, _ = p.communicate()
+        log.append('== %s\n%s' % (s, text))
         if p.returncode != 0:
-            raise RuntimeError('nvcc failed for %s:\n%s' % (s, out))
-    with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
+            raise RuntimeError('nvcc failed for %s:\n%s' % (s, text))
+    with open(os.path.join(LIB_DIR, 'build%s.log' % tag), 'w') as f:
         f.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
-    cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB] + objs + ['-lcudart']
+    target = LIB if out is None else os.path.join(LIB_DIR, os.path.basename(out))
+    cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', target] + objs + ['-lcudart']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout)
-    return LIB
+    return target
 
 
 if __name__ == '__main__':

@@ -10,6 +10,9 @@
 #ifndef SO_RENDER_UNROLL
 #define SO_RENDER_UNROLL 1     // measured 10.20 / 10.56 / 10.44 ms for unroll 1 / 2 / 4 at 8.64 M rays
 #endif
+#ifndef SO_RENDER_BLOCK
+#define SO_RENDER_BLOCK 128
+#endif
 #ifndef SO_RENDER_MIN_CTAS
 #define SO_RENDER_MIN_CTAS 8    // 64 registers, no spills (10 -> 48 registers spills inside the sample loop and is slower)
 #endif
@@ -77,7 +80,7 @@ int launch_depth_bounds(const RayDev& R, const RenderDev& P, float* ws, cudaStre
 // FAST = affine metre->grid map, power-of-two S, cos-anneal finished, mid-point anchor (every shipped eval config):
 // the uniform branches for the general cases are compiled out.
 template <bool HAS_RGB, bool HAS_SEM, bool FAST>
-__global__ void __launch_bounds__(128, SO_RENDER_MIN_CTAS) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+__global__ void __launch_bounds__(SO_RENDER_BLOCK, SO_RENDER_MIN_CTAS) render_infer_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                            const float* __restrict__ bkgd_rand, float* __restrict__ depth,
                                                            float* __restrict__ max_depth, long long* __restrict__ max_idx,
                                                            float* __restrict__ acc_out, float* __restrict__ normal_vis,
@@ -275,12 +278,12 @@ extern "C" int so_render_infer(const float* vol_sdf, const float* vol_feat, cons
 
   if ((rc = launch_depth_bounds(R, P, workspace, st))) return rc;
 
-  unsigned grid = (unsigned)ceil_div64(rd->ray_count, 128);
+  unsigned grid = (unsigned)ceil_div64(rd->ray_count, SO_RENDER_BLOCK);
   ProfScope prof(0, st);
   long long* midx = reinterpret_cast<long long*>(max_idx);
   const bool fast = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f && (P.S & (P.S - 1)) == 0 &&
                     P.cos_anneal == 1.0f && P.anchor_mid;
-#define SO_RENDER(RGB, SEM, F) render_infer_kernel<RGB, SEM, F><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem)
+#define SO_RENDER(RGB, SEM, F) render_infer_kernel<RGB, SEM, F><<<grid, SO_RENDER_BLOCK, 0, st>>>(V, R, P, workspace, bkgd_rand, depth, max_depth, midx, acc, normal_vis, rgb, sem)
   if (want_sem) { if (fast) SO_RENDER(true, true, true); else SO_RENDER(true, true, false); }
   else if (want_rgb) { if (fast) SO_RENDER(true, false, true); else SO_RENDER(true, false, false); }
   else { if (fast) SO_RENDER(false, false, true); else SO_RENDER(false, false, false); }

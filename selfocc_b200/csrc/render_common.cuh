@@ -194,16 +194,8 @@ __device__ __forceinline__ float one_minus_exp_neg(float x) {
 // prev = sdf - half, next = sdf + half (half <= 0).  The difference of the two CDFs is evaluated without
 // cancellation:  Phi(a) - Phi(b) = Phi(a) * Phi(-b) * (1 - exp(-(a - b))),  a - b = -2 * half * inv_s >= 0,
 // which keeps fp32 within rounding of the fp64 evaluation of the reference formula (the reference's own fp32
-// evaluation loses ~3 digits to cancellation here).
-__device__ __forceinline__ float neus_alpha(float sdf, float half, float inv_s) {
-  float hs = half * inv_s, ss = sdf * inv_s;
-  float pa = sigmoid_fast(ss - hs);
-  float diff = pa * sigmoid_fast(-(ss + hs)) * one_minus_exp_neg(-2.0f * hs);
-  return __saturatef(__fdividef(diff + 1e-5f, pa + 1e-5f));
-}
-
-// The same alpha with every exponential taken in base 2: s2 = sdf * inv_s * log2(e), h2 = half * inv_s * log2(e) (<= 0),
-// so each logistic is one ex2.approx + one rcp.approx with no scaling multiply in front.
+// evaluation loses ~3 digits to cancellation here).  Every exponential is taken in base 2:
+// s2 = sdf * inv_s * log2(e), h2 = half * inv_s * log2(e) (<= 0), so each logistic is one ex2.approx + one rcp.approx.
 __device__ __forceinline__ float neus_alpha_log2(float s2, float h2) {
   float pa = __fdividef(1.0f, 1.0f + exp2f(h2 - s2));           // Phi(prev) = 1 / (1 + 2^-(s2 - h2))
   float qb = __fdividef(1.0f, 1.0f + exp2f(s2 + h2));           // Phi(-next)

@@ -10,6 +10,9 @@
 #ifndef SO_ATTN_UNROLL
 #define SO_ATTN_UNROLL 4         // cross-attention: 4.66 / 4.72 / 4.74 ms per step for unroll 4 / 2 / 8
 #endif
+#ifndef SO_SELF_ATTN_MIN_CTAS
+#define SO_SELF_ATTN_MIN_CTAS 4  // 64 registers, no spills: 1.55 ms vs 1.64 ms at 5 CTAs (cross-attention is equal at 4 and 5)
+#endif
 #ifndef SO_SELF_ATTN_UNROLL
 #define SO_SELF_ATTN_UNROLL 8    // self-attention: 1.65 / 1.70 / 1.77 ms per step for unroll 8 / 4 / 2
 #endif
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_cross_attn_kernel(c
 
 // ---- A8 fused cross-view hybrid attention core -----------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(256, SO_ATTN_MIN_CTAS) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+__global__ void __launch_bounds__(256, SO_SELF_ATTN_MIN_CTAS) tpv_self_attn_kernel(const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
                                                             const float* __restrict__ offsets, const float* __restrict__ logits,
                                                             const float* __restrict__ ref, float* __restrict__ out, int Nv, int Hd,
                                                             int Q, int L, int P, int value_ld, int off_ld, int lg_ld) {

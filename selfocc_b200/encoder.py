@@ -6,13 +6,13 @@ The arithmetic of the hot ops runs in ``libselfocc_b200.so``:
 
 * inference (no autograd): one fused kernel per attention -- softmax + sampling-location arithmetic +
   bilinear gather + head sum (+ camera loop / visible-count average for the image cross-attention),
-  no ``nonzero()`` host sync, no padded per-camera rebatch (``ops.tpv_self_attn_forward`` /
-  ``ops.tpv_cross_attn_forward``);
+  no ``nonzero()`` host sync, no padded per-camera rebatch (``ops.tpv_self_attn_forward*`` /
+  ``ops.tpv_cross_attn_forward*``); every dense projection (value / offset / weight / output Linear, FFN) runs on
+  the tcgen05 split-precision GEMM (``ops.linear_3xtf32``, fp32-level accuracy), projections of the same input are
+  fused into one GEMM; LayerNorm is a warp-per-row kernel (``ops.layer_norm``);
 * training (autograd): the mmcv-contract op ``ops.MultiScaleDeformableAttnFunction`` (forward +
   backward kernels) fed by torch softmax / location arithmetic, visible-query lists compacted on the
-  device (``ops.visible_index_lists``).
-
-Dense projections (value/offset/weight/output Linear, FFN) are library GEMMs (cuBLAS via torch).
+  device (``ops.visible_index_lists``); the projections stay ``nn.Linear`` (cuBLAS) on this path.
 """
 import copy
 import math

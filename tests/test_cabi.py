@@ -43,3 +43,29 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         ops.msda_forward(torch.zeros(1, 4, 1, 16), torch.tensor([[2, 2]]), torch.tensor([0]),
                          torch.zeros(1, 1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1))
+
+
+def test_entry_points_reject_bad_arguments_without_a_gpu():
+    """Error behaviour of the C ABI: null pointers / bad sizes return SO_ERR_INVALID_ARG (-1) or SO_ERR_UNSUPPORTED (-2)
+    before any CUDA call is made, so this runs on a CPU-only box."""
+    import ctypes as C
+    from selfocc_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    N = None
+    assert lib.so_msda_forward(N, N, N, N, N, N, 1, 1, 1, 16, 1, 1, 1, N) == -1
+    assert lib.so_msda_backward(N, N, N, N, N, N, N, N, N, 1, 1, 1, 16, 1, 1, 1, N) == -1
+    assert lib.so_linear_3xtf32(N, N, N, N, N, N, 10, 96, 96, 0, N) == -1
+    one = C.c_void_p(16)   # non-null, 16-byte aligned dummy (never dereferenced on these paths)
+    assert lib.so_linear_3xtf32(one, one, one, N, N, one, 10, 96, 100, 0, N) == -2      # K not a multiple of 96
+    assert lib.so_linear_3xtf32(one, one, one, N, N, one, 0, 96, 96, 0, N) == 0         # M = 0: nothing to do
+    assert lib.so_layer_norm(N, N, N, N, N, 4, 96, 1e-5, N) == -1
+    assert lib.so_layer_norm(one, N, one, one, one, 4, 1000, 1e-5, N) == -2
+    assert lib.so_point_sampling(N, N, 1, 1, 1, 1.0, 1.0, N, N, N, N) == -1
+    assert lib.so_render_infer(N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    d = _lib.VolumeDesc()
+    d.H, d.W, d.Z, d.zpitch = 4, 4, 4, 2            # zpitch < Z
+    assert lib.so_field_query(one, N, C.byref(d), one, 1, one, N, N, N) == -1
+    assert lib.so_tpv_decode(one, one, one, 48, one, one, one, one, C.byref(d), one, N, N) == -1   # invalid volume desc
+    assert lib.so_error_string(-2) == b'unsupported configuration'
+    assert lib.so_render_workspace_floats(0) == 2 and lib.so_render_workspace_floats(24) == 48

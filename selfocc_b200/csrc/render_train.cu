@@ -7,6 +7,9 @@
 // transmittance is an exclusive product scan along the sample dimension done with warp shuffles (5 steps per
 // 32-sample chunk + a carried prefix); the backward needs the matching suffix sums and runs the chunks in reverse.
 #include "render_common.cuh"
+#ifndef SO_TRAIN_FWD_MIN_CTAS
+#define SO_TRAIN_FWD_MIN_CTAS 8   // 64 registers: 0.122 ms vs 0.153 ms at 4 CTAs/SM (cfg-5 sizes); the kernel is latency-bound
+#endif
 
 namespace so {
 
@@ -122,7 +125,7 @@ __device__ __forceinline__ void sample_colour(const VolumeDev& V, const RenderDe
 // FAST = affine metre->grid map, S a power of two (multiple of 32), cos-anneal finished, mid-point anchor: lean per-sample
 // path (closed-form jittered edges, interior gather chosen by a warp vote, base-2 alpha), ~2.4x fewer instructions.
 template <bool HAS_RGB, bool HAS_SEM, bool FAST>
-__global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+__global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                                const float* __restrict__ bkgd_rand, TrainOut O) {
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -142,22 +145,27 @@ __global__ void __launch_bounds__(128) render_train_fwd_kernel(VolumeDev V, RayD
     if (HAS_SEM)
       for (int c = 0; c < kMaxSem; ++c) sem_acc[c] = 0.f;
     const float step = 1.0f / (float)S, span = c.tf - c.tn, k_log2 = P.inv_s * 1.4426950408889634f;
+    // the jitter value of the NEXT chunk is requested one iteration ahead, so its DRAM latency is off the critical path
+    float u_cur = (FAST && c.u) ? __ldg(c.u + lane) : 0.f;
     for (int k = 0; k < K; ++k) {
       int s = k * 32 + lane;
       bool live = s < S;
       Sample q;
       if (FAST) {
+        const int s_nxt = s + 32;
+        const float u_nxt = (c.u && s_nxt <= S) ? __ldg(c.u + s_nxt) : 0.f;
         // edge i is re-drawn inside [max(i - 1/2, 0), min(i + 1/2, S)] / S (exact arithmetic for power-of-two S)
-        auto edge = [&](int i) {
+        auto edge = [&](int i, float u) {
           float fi = (float)i;
           float lo_b = fmaxf(fi - 0.5f, 0.f) * step, up_b = fminf(fi + 0.5f, (float)S) * step;
-          float b = c.u ? fmaf(up_b - lo_b, __ldg(c.u + i), lo_b) : fi * step;
+          float b = c.u ? fmaf(up_b - lo_b, u, lo_b) : fi * step;
           return fmaf(b, span, c.tn);
         };
-        float e0 = edge(s);
-        float e_next = edge(k * 32 + 32);                 // warp-uniform: right edge of lane 31
+        float e0 = edge(s, u_cur);
+        float e_next = edge(k * 32 + 32, __shfl_sync(0xffffffffu, u_nxt, 0));   // right edge of lane 31 = first edge of the next chunk
         float e1 = __shfl_down_sync(0xffffffffu, e0, 1);
         if (lane == 31) e1 = e_next;
+        u_cur = u_nxt;
         q.mid = 0.5f * (e0 + e1);
         q.delta = e1 - e0;
         float gh = fmaf(c.gdh, q.mid, c.gh0), gw = fmaf(c.gdw, q.mid, c.gw0), gd = fmaf(c.gdd, q.mid, c.gd0);

@@ -165,9 +165,13 @@ class _Model(nn.Module):
         self.field = field
 
 
+# Options whose semantics live only in the un-vendored sdfstudio fork: rejected at construction when non-default.
+# `return_second_grad` / `use_compact_2nd_grad` are NOT in this list: four of the six shipped TPV configs set them, they
+# only add the `second_grad` training output (SecondGradLoss), so construction, prepare(), render() and forward_occ()
+# work with those configs and only the training-form forward() refuses (see forward()).
 _UNSUPPORTED_DEFAULTS = dict(use_numerical_gradients=False, use_uniform_gradient=False, calculate_online=False,
-                             use_compact_2nd_grad=False, beta_hand_tune=False, estimate_flow=False, disp_sampler=False,
-                             anneal_aabb=False, using_2d_img_feats=False, return_second_grad=False,
+                             beta_hand_tune=False, estimate_flow=False, disp_sampler=False,
+                             anneal_aabb=False, using_2d_img_feats=False,
                              num_samples_importance=0, num_up_sample_steps=0)
 
 
@@ -187,9 +191,8 @@ class NeuSHead(nn.Module):
                  sample_anchor='mid', **kwargs):
         super().__init__()
         given = dict(use_numerical_gradients=use_numerical_gradients, use_uniform_gradient=use_uniform_gradient,
-                     calculate_online=calculate_online, use_compact_2nd_grad=use_compact_2nd_grad,
-                     beta_hand_tune=beta_hand_tune, estimate_flow=estimate_flow, disp_sampler=disp_sampler,
-                     anneal_aabb=anneal_aabb, using_2d_img_feats=using_2d_img_feats, return_second_grad=return_second_grad,
+                     calculate_online=calculate_online, beta_hand_tune=beta_hand_tune, estimate_flow=estimate_flow,
+                     disp_sampler=disp_sampler, anneal_aabb=anneal_aabb, using_2d_img_feats=using_2d_img_feats,
                      num_samples_importance=num_samples_importance, num_up_sample_steps=num_up_sample_steps)
         bad = {k: v for k, v in given.items() if v != _UNSUPPORTED_DEFAULTS[k]}
         if bad:
@@ -208,6 +211,7 @@ class NeuSHead(nn.Module):
         self.print_freq, self.resolution, self.aabb = print_freq, resolution, list(roi_aabb)
         self.return_uniform_sdf, self.return_max_depth = return_uniform_sdf, return_max_depth
         self.return_surface_sdf, self.return_sample_sdf, self.return_sem = return_surface_sdf, return_sample_sdf, return_sem
+        self.return_second_grad = return_second_grad
         if return_sem and color_dims <= 3:
             raise ValueError('return_sem needs color_dims > 3 (3 rgb + semantic logits)')
         self.z_size = self.model.field.mapping.size_d
@@ -311,5 +315,10 @@ class NeuSHead(nn.Module):
 
     def forward(self, representation, metas=None, **kwargs):
         """neus_head.py:473-713 (training form: per-sample weights / ts / deltas / eik_grad)."""
+        if self.return_second_grad:
+            raise NotImplementedError(
+                "return_second_grad=True: the `second_grad` training output is computed inside the un-vendored sdfstudio fork "
+                "(cuda_gridsample_grad2, `use_compact_2nd_grad`) and its definition cannot be recovered from the reference; "
+                "set return_second_grad=False and drop SecondGradLoss to train, or use prepare()/render()/forward_occ()")
         from .head_train import forward_train
         return forward_train(self, representation, metas, **kwargs)

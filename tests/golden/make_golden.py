@@ -123,5 +123,28 @@ def main():
     print('wrote', len(out), 'arrays')
 
 
+
+
+def dump_reference_model_configs():
+    """The lifter / encoder / head config dicts of every shipped TPV experiment config, as the reference's own config
+    files define them (plain `exec` of config/<set>/<name>.py: they are self-contained python apart from `_base_`).
+    Written to tests/golden/reference_model_cfgs.json; tests/test_modules_cpu.py builds the B200 modules from them."""
+    import glob
+    import json
+    out = {}
+    for f in sorted(glob.glob(os.path.join(REF, 'config', '*', '*.py'))):
+        if '_base_' in f:
+            continue
+        ns = {}
+        exec(compile(open(f).read(), f, 'exec'), ns)
+        m = ns['model']
+        if m['encoder']['type'] != 'TPVFormerEncoder':
+            continue                      # nuscenes_occ_bev.py: the BEV-only variant is out of scope (SURVEY.md 2.1)
+        out[os.path.relpath(f, os.path.join(REF, 'config'))] = {k: m[k] for k in ('lifter', 'encoder', 'head')}
+    json.dump(out, open(os.path.join(HERE, 'reference_model_cfgs.json'), 'w'), indent=1, sort_keys=True)
+    print('wrote model configs of', sorted(out))
+
+
 if __name__ == '__main__':
-    sys.exit(main())
+    main()
+    dump_reference_model_configs()

@@ -66,7 +66,8 @@ def test_fork_only_options_are_rejected():
     cfg = _small_cfg()['head']
     cfg.pop('type')
     from selfocc_b200.head import NeuSHead
-    for k, v in (('anneal_aabb', True), ('disp_sampler', True), ('num_samples_importance', 64), ('use_numerical_gradients', True)):
+    for k, v in (('anneal_aabb', True), ('disp_sampler', True), ('num_samples_importance', 64), ('use_numerical_gradients', True),
+                 ('estimate_flow', True), ('beta_hand_tune', True)):
         with pytest.raises(NotImplementedError):
             NeuSHead(**{**cfg, k: v})
     with pytest.raises(NotImplementedError):
@@ -99,3 +100,23 @@ def test_product_mapping_matches_reference_golden(golden):
     d = ring.volume_desc(3)
     assert (d.H, d.W, d.Z, d.zpitch, d.n_feat, d.feat_pitch) == (13, 17, 7, 8, 3, 4)
     assert d.axis[0].offset == 0.0 and d.axis[1].offset == 8.0 and d.axis[2].start == -2.0 and d.axis[2].size1 == 2.0
+
+
+def test_modules_build_from_the_reference_config_dicts():
+    """Drop-in check at the config boundary: the lifter / encoder / head dicts of EVERY shipped TPV experiment config
+    (tests/golden/reference_model_cfgs.json, dumped from the reference's own config files) construct the B200 modules."""
+    import json, os
+    cfgs = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_model_cfgs.json')))
+    assert sorted(cfgs) == ['kitti/kitti_novel_depth.py', 'kitti/kitti_occ.py', 'kitti_raw/kitti_raw_depth.py',
+                            'nuscenes/nuscenes_depth.py', 'nuscenes/nuscenes_novel_depth.py', 'nuscenes/nuscenes_occ.py']
+    for name, c in cfgs.items():
+        lifter, enc, head = build_head(c['lifter']), build_head(c['encoder']), build_head(c['head'])
+        H, W, Z = enc.tpv_size
+        assert lifter.tpv_hw.shape == (1, H * W, 96) and lifter.tpv_zh.shape == (1, Z * H, 96)
+        assert (head.bev_size, head.z_size) == ([H, W], Z)
+        assert enc.ref_3d_hw.shape == (8, H * W, 3) and enc.ref_3d_zh.shape[0] == 48
+        assert head.num_samples == 256 and head.ray_sampler.ray_sample_mode == 'cellular'
+        assert head.model.field.desc.n_feat == c['head']['color_dims']
+        if c['head'].get('return_second_grad'):
+            with pytest.raises(NotImplementedError, match='second_grad'):
+                head.forward(representation=None, metas=None)

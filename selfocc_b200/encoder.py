@@ -137,7 +137,7 @@ class _DeformBase(nn.Module):
         nn.init.constant_(self.value_proj.bias, 0.)
 
 
-def fast_linear(lin, x, relu=False, residual=None):
+def fast_linear(lin, x, relu=False, residual=None, out=None):
     """nn.Linear forward for the inference path: the tcgen05 split-precision GEMM (``so_linear_3xtf32``) when the shape
     allows it (K % 96 == 0), cuBLAS otherwise.  Split weights are cached per parameter version."""
     w = lin.weight
@@ -149,11 +149,15 @@ def fast_linear(lin, x, relu=False, residual=None):
                 ent = (ver,) + ops.split_tf32(w.detach().contiguous())
             lin._so_split = ent
         return ops.linear_3xtf32(x.contiguous(), ent[1], ent[2], lin.bias.detach() if lin.bias is not None else None,
-                                 relu=relu, residual=None if residual is None else residual.contiguous())
-    out = F.linear(x, w, lin.bias)
+                                 relu=relu, residual=None if residual is None else residual.contiguous(), out=out)
+    y = F.linear(x, w, lin.bias)
     if relu:
-        out = F.relu(out)
-    return out if residual is None else out + residual
+        y = F.relu(y)
+    y = y if residual is None else y + residual
+    if out is not None:
+        out.copy_(y.view_as(out))
+        return out
+    return y
 
 
 def fast_linear_cat(owner, key, lins, x):
@@ -315,11 +319,12 @@ class BEVCrossAttention(nn.Module):
         nn.init.constant_(self.output_proj.bias, 0.)
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None,
-                bev_masks=None, level_start_index=None, bev_vis=None, value_rows=None, **kwargs):
+                bev_masks=None, level_start_index=None, bev_vis=None, value_rows=None, out_rows=None, **kwargs):
         """query [B,Q,C]; key/value [N, sum(hw), B, C]; reference_points_cams [N,B,Q,D,2];
         bev_masks [N,B,Q,D] (bool/uint8); bev_vis optional uint8 [N,Q] = any_D(mask) from so_point_sampling;
         value_rows optional [N*sum(hw), >= C] view holding value_proj(value) already (TPVCrossAttention projects the image
-        features for its three planes in one GEMM)."""
+        features for its three planes in one GEMM); out_rows optional contiguous [Q, C] destination (a row range of the
+        layer's concatenated token buffer, so the three planes need no torch.cat afterwards)."""
         if key is None:
             key = query
         if value is None:
@@ -347,7 +352,7 @@ class BEVCrossAttention(nn.Module):
                                                    offsets, logits, uv, bev_vis.contiguous())
             if self.training:
                 return self.dropout(fast_linear(self.output_proj, slots))[None] + residual
-            return fast_linear(self.output_proj, slots, residual=residual[0])[None]
+            return fast_linear(self.output_proj, slots, residual=residual[0], out=out_rows)[None]
         slots = self._rebatch_forward(query, value, spatial_shapes, reference_points_cams, bev_masks, level_start_index)
         slots = self.output_proj(slots)
         return self.dropout(slots) + residual
@@ -396,16 +401,24 @@ class TPVCrossAttention(nn.Module):
         self.attns = [self.attn_hw, self.attn_zh, self.attn_wz]
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None, tpv_masks=None,
-                level_start_index=None, tpv_vis=None, **kwargs):
+                level_start_index=None, tpv_vis=None, out_cat=None, **kwargs):
         rows = [None, None, None]
         vps = [a.deformable_attention.value_proj for a in self.attns]
         if value.shape[2] == 1 and _fusable(vps, value) and not _needs_grad(value, query[0], vps[0].weight):
             # the three planes project the SAME image features with their own value_proj: one GEMM, three column slices
             _, rows = fast_linear_cat(self, '_so_value3', vps, value[:, :, 0].reshape(-1, value.shape[-1]))
+        outs = [None, None, None]
+        if out_cat is not None:                       # [1, Q_hw + Q_zh + Q_wz, C] token buffer of the layer
+            o0 = 0
+            for i in range(3):
+                n = query[i].shape[1]
+                outs[i] = out_cat[0, o0:o0 + n]
+                o0 += n
         return [self.attns[i](query[i], key, value, residual[i] if residual is not None else None,
                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                               reference_points_cams=reference_points_cams[i], bev_masks=tpv_masks[i],
-                              bev_vis=None if tpv_vis is None else tpv_vis[i], value_rows=rows[i]) for i in range(3)]
+                              bev_vis=None if tpv_vis is None else tpv_vis[i], value_rows=rows[i], out_rows=outs[i])
+                for i in range(3)]
 
 
 class FFN(nn.Module):
@@ -435,6 +448,20 @@ class FFN(nn.Module):
 
 if not HAVE_MMENGINE:  # mmcv registers its own FFN when present
     MODELS.register_module(name='FFN', module=FFN)
+
+
+def _whole(views, split):
+    """The concatenated [B, sum(split), C] tensor when `views` are exactly its torch.split pieces, else None."""
+    base = getattr(views[0], '_base', None)
+    if base is None or base.dim() != 3 or base.shape[1] != sum(split) or not base.is_contiguous():
+        return None
+    off = 0
+    for v, n in zip(views, split):
+        if v._base is not base or v.shape[1] != n or v.data_ptr() != base.data_ptr() + off * base.shape[2] * base.element_size() \
+                or base.shape[0] != 1:
+            return None
+        off += n
+    return base
 
 
 @MODELS.register_module()
@@ -490,34 +517,46 @@ class TPVFormerLayer(nn.Module):
             ss = torch.tensor([[H, W], [Z, H], [W, Z]], device=dev)
             tpv_levels = (ss, torch.tensor([0, H * W, H * W + Z * H], device=dev))
         pos_cat = torch.cat(tpv_pos, dim=1) if isinstance(tpv_pos, (list, tuple)) else tpv_pos
+        # `qc` is the concatenated [B, Q_hw + Q_zh + Q_wz, C] token buffer; `query` are its per-plane views.  Keeping both
+        # avoids the reference's torch.cat before every self-attention / norm / ffn step (5 x 31 MB copies per layer).
+        qc = _whole(query, split)
+        cat = lambda views, whole: whole if whole is not None else torch.cat(views, dim=1)
         for op in self.operation_order:
             if op == 'self_attn':
-                q = torch.cat(query, dim=1)
-                q = self.attentions[attn_i](q, q, q, torch.cat(identity, dim=1) if self.pre_norm else None,
-                                            query_pos=pos_cat, reference_points=ref_2d, spatial_shapes=tpv_levels[0],
-                                            level_start_index=tpv_levels[1], **kwargs)
-                query = torch.split(q, split, 1)
+                q = cat(query, qc)
+                idt = (q if identity is query else torch.cat(identity, dim=1)) if self.pre_norm else None
+                qc = self.attentions[attn_i](q, q, q, idt, query_pos=pos_cat, reference_points=ref_2d,
+                                             spatial_shapes=tpv_levels[0], level_start_index=tpv_levels[1], **kwargs)
+                query = torch.split(qc, split, 1)
                 attn_i += 1
                 identity = query
             elif op == 'norm':
-                q = torch.cat(query, dim=1)
+                q = cat(query, qc)
                 ln = self.norms[norm_i]
                 if q.is_cuda and q.dtype == torch.float32 and q.shape[-1] <= 256 and not _needs_grad(q, ln.weight):
-                    q = ops.layer_norm(q.contiguous(), ln.weight.detach(), ln.bias.detach(), ln.eps)
+                    qc = ops.layer_norm(q.contiguous(), ln.weight.detach(), ln.bias.detach(), ln.eps)
                 else:
-                    q = ln(q)
-                query = torch.split(q, split, 1)
+                    qc = ln(q)
+                query = torch.split(qc, split, 1)
                 norm_i += 1
             elif op == 'cross_attn':
-                query = self.attentions[attn_i](query, key, value, identity if self.pre_norm else None,
-                                                spatial_shapes=spatial_shapes, level_start_index=level_start_index,
-                                                reference_points_cams=reference_points_cams, tpv_masks=tpv_masks,
-                                                tpv_vis=tpv_vis, **kwargs)
+                fused = query[0].is_cuda and not self.training and not _needs_grad(query[0], key)
+                buf = query[0].new_empty(1, sum(split), query[0].shape[-1]) if (fused and query[0].shape[0] == 1) else None
+                outs = self.attentions[attn_i](query, key, value, identity if self.pre_norm else None,
+                                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                                               reference_points_cams=reference_points_cams, tpv_masks=tpv_masks,
+                                               tpv_vis=tpv_vis, out_cat=buf, **kwargs)
+                if buf is not None and all(o.data_ptr() == v.data_ptr() for o, v in zip(outs, torch.split(buf, split, 1))):
+                    qc, query = buf, torch.split(buf, split, 1)       # the three planes were written in place
+                else:
+                    qc, query = None, outs
                 attn_i += 1
                 identity = query
             elif op == 'ffn':
-                q = self.ffns[ffn_i](torch.cat(query, dim=1), torch.cat(identity, dim=1) if self.pre_norm else None)
-                query = torch.split(q, split, 1)
+                q = cat(query, qc)
+                idt = (q if identity is query else torch.cat(identity, dim=1)) if self.pre_norm else None
+                qc = self.ffns[ffn_i](q, idt)
+                query = torch.split(qc, split, 1)
                 ffn_i += 1
         return query
 

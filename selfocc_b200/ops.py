@@ -373,16 +373,21 @@ def split_tf32(w):
     return hi, lo
 
 
-def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None):
-    """y = act(x @ w^T + bias) (+ residual) on tcgen05 tensor cores with fp32-level accuracy.  x [..., K] contiguous."""
+def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None, out=None):
+    """y = act(x @ w^T + bias) (+ residual) on tcgen05 tensor cores with fp32-level accuracy.  x [..., K] contiguous.
+    ``out``: optional pre-allocated contiguous [..., N] destination (e.g. a row range of a larger token buffer)."""
     lib = _lib.load()
     _chk(x, name='x'); _chk(w_hi, name='w_hi'); _chk(w_lo, name='w_lo'); _chk(bias, name='bias'); _chk(residual, name='residual')
     N, K = w_hi.shape
     assert x.shape[-1] == K
     M = x.numel() // K
-    y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    if out is None:
+        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    else:
+        y = _chk(out, name='out')
+        assert y.numel() == M * N and y.shape[-1] == N
     if residual is not None:
-        assert residual.shape == y.shape
+        assert residual.numel() == y.numel()
     _lib.check(lib.so_linear_3xtf32(_p(x), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(y), M, N, K, int(bool(relu)), _stream()),
                'so_linear_3xtf32')
     return y

@@ -141,13 +141,21 @@ int so_render_infer(const float* vol_sdf, const float* vol_feat, const so_volume
  * backward.  `jitter` [total rays, S+1] uniforms in [0,1) for the stratified sampler (`perturb=True`), NULL =
  * no jitter.  Per-ray outputs [n]: depth, acc, fars (far / |dir|), max_depth, rgb [n,3], sem [n,n_feat-3];
  * per-sample outputs [n,S]: weights, ts = mid / |dir|, deltas = (end-start) / |dir|, sample_sdf; eik_grad [n,S,3]
- * = d sdf / d metre at the samples.  Any output may be NULL.  S <= 256. */
+ * = d sdf / d metre at the samples.  Any output may be NULL.  S <= 256.
+ * pair_workspace: optional scratch of so_render_train_pair_floats(vol) floats (8-byte aligned), NULL = none.  When
+ * given, the sdf volume is first repacked as {v[z], v[z+1]} pairs so that the 8 trilinear taps become 4 aligned
+ * 64-bit loads (half the L1 requests of the gather-bound forward); results are bit-identical either way. */
+int64_t so_render_train_pair_floats(const so_volume_desc* vol_host);
 int so_render_train_forward(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
                             const float* cam_mats, const float* pix, const so_ray_desc* rays_host,
                             const so_render_params* params_host, const float* jitter, const float* bkgd_rand,
                             float* depth, float* acc, float* fars, float* rgb, float* sem, float* max_depth,
                             float* weights, float* ts, float* deltas, float* eik_grad, float* sample_sdf,
-                            float* workspace, void* stream);
+                            float* workspace, float* pair_workspace, void* stream);
+
+/* Test hook: force the one-ray-per-warp forward kernel (default: the batched-ray kernel whenever the mapping is affine,
+ * num_samples is a power of two >= 64, the cos-anneal is finished and no semantics are rendered). */
+int so_render_train_force_fwd32(int on);
 
 /* Backward of so_render_train_forward w.r.t. the decoded volume and inv_s.  Incoming gradients (NULL = zero):
  * g_depth, g_acc [n], g_rgb [n,3], g_sem [n,n_feat-3], g_weights, g_sdf [n,S], g_eik [n,S,3].  Results are

@@ -11,6 +11,10 @@ from selfocc_b200.mapping import GridMeterMapping
 ap = argparse.ArgumentParser()
 ap.add_argument('--cf', type=int, default=25)
 ap.add_argument('--iters', type=int, default=20)
+ap.add_argument('--fwd-only', action='store_true', help='time the forward kernel only (no backward pass)')
+ap.add_argument('--fwd32', action='store_true', help='force the 32-samples-per-warp-step forward kernel')
+ap.add_argument('--no-pair', action='store_true', help='gather from the sdf volume itself (no z-pair repack)')
+ap.add_argument('--tag', default='')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 margs = dict(synth.NUSC_MAPPING, d_size=[24, 0], d_range=[-4.0, 4.0, 4.0])
@@ -32,8 +36,10 @@ invs = torch.tensor([20.0], device=dev, requires_grad=True)
 want = ['depth', 'acc', 'fars', 'weights', 'ts', 'deltas', 'eik_grad'] + (['rgb'] if n_feat >= 3 else []) + (['sem'] if n_feat > 3 else [])
 cfg = dict(desc=desc, cam_mats=i2l, rays=ops.make_ray_desc(6, grid=(ny, nx, 16.0, 3.0, 16.0, 5.0)),
            params=ops.make_render_params(aabb, S, 20.0, training=True, bkgd='random' if n_feat else 'white'), jitter=jit,
-           bkgd_rand=bk if n_feat else None, want=want)
+           bkgd_rand=bk if n_feat else None, want=want, zpair=not a.no_pair)
 _lib.profile_enable(True)
+if a.fwd32:
+    _lib.load().so_render_train_force_fwd32(1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for it in range(a.iters + 3):
     if it == 3:
@@ -42,17 +48,18 @@ for it in range(a.iters + 3):
     res = dict(zip(ops.RenderTrainFunction.ORDER, ops.RenderTrainFunction.apply(vs, vf, invs, cfg)))
     loss = res['depth'].sum() + res['weights'].sum() + res['eik_grad'].sum() + (res['rgb'].sum() if n_feat >= 3 else 0) \
         + (res['sem'].sum() if n_feat > 3 else 0)
-    loss.backward()
+    if not a.fwd_only:
+        loss.backward()
 torch.cuda.synchronize()
 prof = _lib.profile_read()
 peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
 peak = float(peaks.get('hbm_gbs', 6650.0))
 fwd_ms = prof['render_train_fwd'][0] / prof['render_train_fwd'][1]
-bwd_ms = prof['render_train_bwd'][0] / prof['render_train_bwd'][1]
+bwd_ms = prof['render_train_bwd'][0] / max(prof['render_train_bwd'][1], 1) if 'render_train_bwd' in prof else float('nan')
 out_bytes = n * (S * (4 + 4 + 4 + 12) + 4 * 3 + (12 if n_feat >= 3 else 0) + 4 * max(n_feat - 3, 0))
 in_bytes = n * (S + 1) * 4 + desc.H * desc.W * desc.zpitch * 4 + (desc.H * desc.W * desc.Z * desc.feat_pitch * 4 if n_feat else 0)
 fwd_gbs = (out_bytes + in_bytes) / (fwd_ms * 1e-3) / 1e9
-print(json.dumps({'kernel': 'render_train_fwd_kernel', 'workload': 'nuscenes_occ_train 6x48x100 rays x256, Cf=%d' % a.cf,
+print(json.dumps({'kernel': 'render_train_fwd_kernel' if a.fwd32 else 'render_train_fwd5_kernel (+ zpair_pack_kernel)', 'tag': a.tag, 'lib': os.environ.get('SELFOCC_B200_LIB', 'default'), 'workload': 'nuscenes_occ_train 6x48x100 rays x256, Cf=%d' % a.cf,
                   'rays': n, 'fwd_ms': fwd_ms, 'bwd_ms': bwd_ms, 'algorithmic_bytes_fwd': out_bytes + in_bytes,
                   'roofline': {'bound': 'hbm', 'achieved': fwd_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': fwd_gbs / peak},
                   'rays_per_s_fwd': n / (fwd_ms * 1e-3), 'rays_per_s_fwd_bwd': n / ((fwd_ms + bwd_ms) * 1e-3)}))

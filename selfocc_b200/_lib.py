@@ -49,11 +49,13 @@ SIGNATURES = {
     'so_profile_elapsed_ms': (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     'so_tpv_decode': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _P, _P, _P]),
     'so_tpv_decode_force_simt': (C.c_int, [C.c_int]),
+    'so_render_train_force_fwd32': (C.c_int, [C.c_int]),
     'so_render_workspace_floats': (C.c_int64, [_L]),
     'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'so_render_train_forward': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
-                                          _P, _P] + [_P] * 11 + [_P, _P]),
+                                          _P, _P] + [_P] * 11 + [_P, _P, _P]),
+    'so_render_train_pair_floats': (_L, [C.POINTER(VolumeDesc)]),
     'so_render_train_backward': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                            _P, _P] + [_P] * 7 + [_P, _P, _P, _P, _P]),
     'so_field_query_backward': (C.c_int, [C.POINTER(VolumeDesc), _P, _L, _P, _P, _P, _P, _P, _P]),

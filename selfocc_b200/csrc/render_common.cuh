@@ -200,7 +200,11 @@ __device__ __forceinline__ float neus_alpha_log2(float s2, float h2) {
   float pa = __fdividef(1.0f, 1.0f + exp2f(h2 - s2));           // Phi(prev) = 1 / (1 + 2^-(s2 - h2))
   float qb = __fdividef(1.0f, 1.0f + exp2f(s2 + h2));           // Phi(-next)
   float x = h2 * (-2.0f * 0.6931471805599453f);                 // a - b in natural units (>= 0)
+#ifdef SO_ALPHA_HORNER
+  float ser = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 120.0f, -1.0f / 24.0f), 1.0f / 6.0f), -0.5f), 1.0f);   // same polynomial, 5 ops
+#else
   float ser = x * (1.0f - x * 0.5f * (1.0f - x * (1.0f / 3.0f) * (1.0f - x * 0.25f * (1.0f - x * 0.2f))));
+#endif
   float omen = x < 0.125f ? ser : 1.0f - exp2f(2.0f * h2);
   return __saturatef(__fdividef(fmaf(pa * qb, omen, 1e-5f), pa + 1e-5f));
 }

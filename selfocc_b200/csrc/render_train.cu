@@ -258,6 +258,280 @@ __global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_k
   }
 }
 
+// ---- forward, batched rays + U chunks in flight + z-pair volume ---------------------------------------------------
+// Same contract and the same per-sample arithmetic as render_train_fwd_kernel<., false, true> (lane = sample, so the 32
+// lanes of a load touch neighbouring voxels: the gathers are bound by distinct 128-byte lines per L1 request), with the
+// three things ncu showed that kernel to lack:
+//  (a) a warp takes a BATCH of consecutive rays: lane b computes ray b's set-up (camera ray, slab test, affine
+//      grid-space ray: ~300 instructions the one-ray-per-warp kernel repeats in all 32 lanes) and, after the batch, its
+//      tail (depth clip, divisions, per-ray stores); the 12 per-ray constants are broadcast with shuffles;
+//  (b) U chunks (32 U samples) are evaluated per loop iteration, so 8 U (4 U with the pair volume) independent gathers
+//      are in flight per thread instead of 8;
+//  (c) PAIR: the sdf volume is first repacked as float2 {v[z], v[z + 1]} (zpair_pack_kernel, 2 x 8 MB, L2 resident),
+//      which turns the 8 taps into 4 aligned 64-bit loads: half the L1 requests and half the tag look-ups.
+// The jittered edge b_i = lo_i + (up_i - lo_i) u_i of the upstream sampler is evaluated as
+// fma(w_i, u_i, max(i - 1/2, 0)) * step with w_i = 1 (1/2 at the two ends); for power-of-two S this is the same
+// fp32 value as the one-ray-per-warp kernel's.
+#ifndef SO_TRAIN_FWD5_U
+#define SO_TRAIN_FWD5_U 4            // measured (cfg-5 sizes, us): U=1 137, U=2 119, U=4 109 -- the kernel is latency-bound
+#endif
+#ifndef SO_TRAIN_FWD5_PREFETCH
+#define SO_TRAIN_FWD5_PREFETCH 1     // 1 / 2: prefetch.global.L2 / .L1 of the batch's jitter rows before the ray set-up (109 -> 101 us)
+#endif
+#ifndef SO_TRAIN_FWD5_AHEAD
+#define SO_TRAIN_FWD5_AHEAD 1        // 1: the jitter of group k + 1 is requested while group k is evaluated (101 -> 98 us)
+#endif
+#ifndef SO_TRAIN_FWD5_WARPS
+#define SO_TRAIN_FWD5_WARPS 4
+#endif
+#ifndef SO_TRAIN_FWD5_MIN_CTAS
+#define SO_TRAIN_FWD5_MIN_CTAS 4
+#endif
+#ifndef SO_TRAIN_FWD5_BATCH
+#define SO_TRAIN_FWD5_BATCH 4
+#endif
+#ifndef SO_TRAIN_FWD5_CONST_PITCH
+#define SO_TRAIN_FWD5_CONST_PITCH 1  // specialise for zpitch 32, W 257 (every nuScenes config): the taps = 1 address + immediates
+#endif
+
+__device__ __forceinline__ void prefetch_global(const void* p) {
+#if SO_TRAIN_FWD5_PREFETCH == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(p)));
+#endif
+}
+
+__global__ void __launch_bounds__(256) zpair_pack_kernel(const float* __restrict__ v, float2* __restrict__ out, long long n, int zp) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int z = (int)(i % zp);
+  out[i] = make_float2(v[i], z + 1 < zp ? v[i + 1] : 0.f);
+}
+
+// ZP / WZP: compile-time zpitch and W * zpitch (0 = take them from the descriptor)
+template <bool HAS_RGB, bool PAIR, int ZP, int WZP>
+__global__ void __launch_bounds__(32 * SO_TRAIN_FWD5_WARPS, SO_TRAIN_FWD5_MIN_CTAS)
+render_train_fwd5_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws, const float2* __restrict__ vpair,
+                         const float* __restrict__ bkgd_rand, TrainOut O) {
+  constexpr int B = SO_TRAIN_FWD5_BATCH, U = SO_TRAIN_FWD5_U;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int S = P.S;
+  const int K = S >> 5;                    // the launcher guarantees S % (32 U) == 0
+  const float eps = 1.1920928955078125e-07f;
+  const float k_log2 = P.inv_s * 1.4426950408889634f;
+  const float kh = V.ax[0].k0, kw = V.ax[1].k0, kd = V.ax[2].k0;
+  const int zp = ZP ? ZP : V.zpitch, wzp = WZP ? WZP : V.W * V.zpitch;
+  const bool want_max = O.max_depth != nullptr;
+  const long long n_batches = (R.ray_count + B - 1) / B;
+  for (long long batch = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); batch < n_batches; batch += warps) {
+    const long long ray0 = batch * B;
+    const int nb = (int)min((long long)B, R.ray_count - ray0);
+    if (SO_TRAIN_FWD5_PREFETCH && P.jitter) {     // the batch's jitter rows are contiguous: one line per lane, before the set-up
+      const char* jb = reinterpret_cast<const char*>(P.jitter + (R.ray_begin + ray0) * (long long)(S + 1));
+      const long long span = (long long)nb * (S + 1) * 4;
+      for (long long off = lane * 128LL; off < span; off += 32 * 128) prefetch_global(jb + off);
+      if (lane == 0) prefetch_global(jb + span - 4);
+    }
+    // ---- set-up of ray (ray0 + lane) in lane `lane` (lanes >= nb repeat the batch's first ray: no divergence, unused)
+    const bool own = lane < nb;
+    const long long my_ray = own ? ray0 + lane : ray0;
+    const long long my_gid = R.ray_begin + my_ray;
+    RayCtx c;
+    make_ctx(V, R, P, my_gid, c);
+    const float my_span_s = (c.tf - c.tn) * (1.0f / (float)S);      // exact: 1/S is a power of two
+    float r_acc = 0.f, r_dsum = 0.f, r_best = 0.f, r_cr = 0.f, r_cg = 0.f, r_cb = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const long long ray = ray0 + b;
+      const float d0 = __shfl_sync(kFull, c.d[0], b), d1 = __shfl_sync(kFull, c.d[1], b), d2 = __shfl_sync(kFull, c.d[2], b);
+      const float inv_nrm = __shfl_sync(kFull, c.inv_nrm, b), tn = __shfl_sync(kFull, c.tn, b), span_s = __shfl_sync(kFull, my_span_s, b);
+      const float gh0 = __shfl_sync(kFull, c.gh0, b), gdh = __shfl_sync(kFull, c.gdh, b);
+      const float gw0 = __shfl_sync(kFull, c.gw0, b), gdw = __shfl_sync(kFull, c.gdw, b);
+      const float gd0 = __shfl_sync(kFull, c.gd0, b), gdd = __shfl_sync(kFull, c.gdd, b);
+      const float* __restrict__ u = P.jitter ? P.jitter + (R.ray_begin + ray) * (long long)(S + 1) : nullptr;
+      float carry = 1.0f, acc = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+      float best = -INFINITY, best_ts = 0.f;
+      int best_i = 0x7fffffff;
+#if SO_TRAIN_FWD5_AHEAD
+      float ucur[U], unx = 0.f;           // jitter of the current group's samples / of the first edge of the next group
+#pragma unroll
+      for (int j = 0; j < U; ++j) ucur[j] = u ? __ldcs(u + (j << 5) + lane) : 0.f;
+      if (u) unx = __ldcs(u + (U << 5));
+#endif
+      for (int k = 0; k < K; k += U) {
+        // ---- left bin edges (ray length) of this lane's U samples, and the first edge of the next group
+        float e0[U];
+        const int inx = (k + U) << 5;               // <= S; the jitter row has S + 1 entries
+        float bnx = (float)inx;
+#if SO_TRAIN_FWD5_AHEAD
+        float unext[U], unx2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < U; ++j) unext[j] = 0.f;
+        if (u && k + U < K) {                       // then (k + 2 U) * 32 <= S
+#pragma unroll
+          for (int j = 0; j < U; ++j) unext[j] = __ldcs(u + ((k + U + j) << 5) + lane);
+          unx2 = __ldcs(u + ((k + 2 * U) << 5));
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int s = ((k + j) << 5) + lane;
+          const float fs = (float)s;
+          float bb = fs;
+          if (u) bb = s == 0 ? 0.5f * ucur[j] : ucur[j] + (fs - 0.5f);
+          e0[j] = fmaf(bb, span_s, tn);
+          ucur[j] = unext[j];
+        }
+        if (u) bnx = inx == S ? fmaf(0.5f, unx, bnx - 0.5f) : unx + (bnx - 0.5f);
+        unx = unx2;
+#else
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int s = ((k + j) << 5) + lane;
+          const float fs = (float)s;
+          float bb = fs;
+          if (u) { float uu = __ldcs(u + s); bb = s == 0 ? 0.5f * uu : uu + (fs - 0.5f); }
+          e0[j] = fmaf(bb, span_s, tn);
+        }
+        if (u) { float un = __ldcs(u + inx); bnx = inx == S ? fmaf(0.5f, un, bnx - 0.5f) : un + (bnx - 0.5f); }
+#endif
+        const float e_next = fmaf(bnx, span_s, tn);
+        // ---- positions in grid space
+        float mid[U], delta[U], fh[U], fw[U], fz[U], gh[U], gw[U], gd[U];
+        int h0[U], w0[U], z0[U];
+        bool interior = true;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          // right edge = left edge of the next sample: lane l + 1, or lane 0 of the next chunk for lane 31
+          const float src = lane == 0 ? (j + 1 < U ? e0[j + 1 < U ? j + 1 : j] : e_next) : e0[j];
+          const float e1 = __shfl_sync(kFull, src, (lane + 1) & 31);
+          mid[j] = 0.5f * (e0[j] + e1);
+          delta[j] = e1 - e0[j];
+          gh[j] = fmaf(gdh, mid[j], gh0); gw[j] = fmaf(gdw, mid[j], gw0); gd[j] = fmaf(gdd, mid[j], gd0);
+          float flh = floorf(gh[j]), flw = floorf(gw[j]), flz = floorf(gd[j]);
+          h0[j] = (int)flh; w0[j] = (int)flw; z0[j] = (int)flz;
+          fh[j] = gh[j] - flh; fw[j] = gw[j] - flw; fz[j] = gd[j] - flz;
+          interior = interior && (unsigned)h0[j] < (unsigned)(V.H - 1) && (unsigned)w0[j] < (unsigned)(V.W - 1) &&
+                     (unsigned)z0[j] < (unsigned)(V.Z - 1);
+        }
+        // ---- field: trilinear sdf + analytic gradient
+        float sdf[U], gx[U], gy[U], gz[U], alpha[U];
+        if (__all_sync(kFull, interior)) {
+          float a[U][8];
+#pragma unroll
+          for (int j = 0; j < U; ++j) {               // every load of the group is issued before the first use
+            const int idx = h0[j] * wzp + w0[j] * zp + z0[j];
+            if (PAIR) {
+              const float2* q00 = vpair + idx;
+              float2 v00 = __ldg(q00), v01 = __ldg(q00 + zp), v10 = __ldg(q00 + wzp), v11 = __ldg(q00 + wzp + zp);
+              a[j][0] = v00.x; a[j][1] = v00.y; a[j][2] = v01.x; a[j][3] = v01.y;
+              a[j][4] = v10.x; a[j][5] = v10.y; a[j][6] = v11.x; a[j][7] = v11.y;
+            } else {
+              const float* p00 = V.sdf + idx;
+              a[j][0] = __ldg(p00); a[j][1] = __ldg(p00 + 1);
+              a[j][2] = __ldg(p00 + zp); a[j][3] = __ldg(p00 + zp + 1);
+              a[j][4] = __ldg(p00 + wzp); a[j][5] = __ldg(p00 + wzp + 1);
+              a[j][6] = __ldg(p00 + wzp + zp); a[j][7] = __ldg(p00 + wzp + zp + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            float dz00 = a[j][1] - a[j][0], dz01 = a[j][3] - a[j][2], dz10 = a[j][5] - a[j][4], dz11 = a[j][7] - a[j][6];
+            float c00 = fmaf(fz[j], dz00, a[j][0]), c01 = fmaf(fz[j], dz01, a[j][2]);
+            float c10 = fmaf(fz[j], dz10, a[j][4]), c11 = fmaf(fz[j], dz11, a[j][6]);
+            float dw0 = c01 - c00, dw1 = c11 - c10;
+            float c0 = fmaf(fw[j], dw0, c00), c1 = fmaf(fw[j], dw1, c10);
+            float dz0 = fmaf(fw[j], dz01 - dz00, dz00), dz1 = fmaf(fw[j], dz11 - dz10, dz10);
+            float dgh = c1 - c0;
+            sdf[j] = fmaf(fh[j], dgh, c0);
+            gy[j] = dgh * kh;
+            gx[j] = fmaf(fh[j], dw1 - dw0, dw0) * kw;
+            gz[j] = fmaf(fh[j], dz1 - dz0, dz0) * kd;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            Taps t = make_taps(V, gh[j], gw[j], gd[j]);
+            float dgh, dgw, dgd;
+            gather_sdf(V, t, sdf[j], dgh, dgw, dgd);
+            gx[j] = dgw * kw; gy[j] = dgh * kh; gz[j] = dgd * kd;
+          }
+        }
+        // ---- NeuS alpha
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          float tc = d0 * gx[j] + d1 * gy[j] + d2 * gz[j];
+          alpha[j] = neus_alpha_log2(sdf[j] * k_log2, fminf(tc, 0.f) * (delta[j] * (0.5f * k_log2)));
+        }
+        // ---- transmittance (one warp product scan per chunk), per-sample outputs (streaming stores), ray sums
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int s = ((k + j) << 5) + lane;
+          float f = 1.0f - alpha[j] + 1e-7f;
+          float incl = warp_incl_prod(f, lane);
+          float excl = __shfl_up_sync(kFull, incl, 1);
+          float T = carry * (lane == 0 ? 1.0f : excl);
+          carry *= __shfl_sync(kFull, incl, 31);
+          float w = alpha[j] * T;
+          const long long oidx = ray * S + s;
+          float ts = mid[j] * inv_nrm, dl = delta[j] * inv_nrm;      // neus_head.py:571-577 (reciprocal multiply, <= 1 ulp)
+          if (O.weights) __stcs(O.weights + oidx, w);
+          if (O.ts) __stcs(O.ts + oidx, ts);
+          if (O.deltas) __stcs(O.deltas + oidx, dl);
+          if (O.sdf) __stcs(O.sdf + oidx, sdf[j]);
+          if (O.eik) { __stcs(O.eik + 3 * oidx, gx[j]); __stcs(O.eik + 3 * oidx + 1, gy[j]); __stcs(O.eik + 3 * oidx + 2, gz[j]); }
+          acc += w;
+          dsum = fmaf(w, mid[j], dsum);
+          if (want_max) {
+            float cand = (dl < eps ? 0.f : w) * __fdividef(1.0f, fmaxf(dl, eps));  // neus_head.py:579-587
+            if (cand > best) { best = cand; best_i = s; best_ts = ts; }
+          }
+          if (HAS_RGB) {
+            float col[3], raw[3];
+            Taps t = make_taps(V, gh[j], gw[j], gd[j]);
+            sample_colour(V, P, t, col, raw);
+            cr = fmaf(w, col[0], cr); cg = fmaf(w, col[1], cg); cb = fmaf(w, col[2], cb);
+          }
+        }
+      }
+      acc = warp_sum(acc);
+      dsum = warp_sum(dsum);
+      if (want_max) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {   // first-max argmax: larger score wins, ties go to the smaller sample index
+          float ob = __shfl_xor_sync(kFull, best, off);
+          int oi = __shfl_xor_sync(kFull, best_i, off);
+          float ot = __shfl_xor_sync(kFull, best_ts, off);
+          if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_ts = ot; }
+        }
+      }
+      if (HAS_RGB) { cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); }
+      if (lane == b) { r_acc = acc; r_dsum = dsum; r_best = best_ts; if (HAS_RGB) { r_cr = cr; r_cg = cg; r_cb = cb; } }
+    }
+    // ---- per-ray tail of ray (ray0 + lane)
+    if (own) {
+      const long long ray = my_ray;
+      long long chunk = R.chunk_len > 0 ? my_gid / R.chunk_len : 0;
+      float lo = ws[2 * chunk], hi = ws[2 * chunk + 1];
+      float dd = fminf(fmaxf(r_dsum / (r_acc + 1e-10f), lo), hi);
+      if (O.depth) O.depth[ray] = dd / c.nrm;
+      if (O.acc) O.acc[ray] = r_acc;
+      if (O.fars) O.fars[ray] = c.tf / c.nrm;
+      if (O.max_depth) O.max_depth[ray] = r_best;
+      if (HAS_RGB && O.rgb) {
+        float b0, b1, b2;
+        if (P.bkgd_mode == 2) { b0 = bkgd_rand[3 * ray]; b1 = bkgd_rand[3 * ray + 1]; b2 = bkgd_rand[3 * ray + 2]; }
+        else { b0 = b1 = b2 = (P.bkgd_mode == 1) ? 1.f : 0.f; }
+        float rem = 1.0f - r_acc;
+        float r = fmaf(b0, rem, r_cr), g = fmaf(b1, rem, r_cg), bb = fmaf(b2, rem, r_cb);
+        if (P.eval_clamp) { r = __saturatef(r); g = __saturatef(g); bb = __saturatef(bb); }
+        O.rgb[3 * ray] = r; O.rgb[3 * ray + 1] = g; O.rgb[3 * ray + 2] = bb;
+      }
+    }
+  }
+}
+
 // scatter d(loss)/d(sdf value), d/d(metre-gradient) of one sample into the 8 corners of the sdf volume
 __device__ __forceinline__ void scatter_sdf(const VolumeDev& V, float* __restrict__ gvol, const Taps& t, float g_s, float g_gh,
                                             float g_gw, float g_gd) {
@@ -453,13 +727,23 @@ static int train_common_checks(const float* vol_sdf, const float* vol_feat, cons
 
 using namespace so;
 
+static bool g_force_fwd32 = false;
+// test hook: route so_render_train_forward through the one-ray-per-warp kernel even when the batched one applies
+extern "C" int so_render_train_force_fwd32(int on) { g_force_fwd32 = on != 0; return SO_OK; }
+
+extern "C" int64_t so_render_train_pair_floats(const so_volume_desc* vol_host) {
+  if (!vol_host || validate_volume(vol_host)) return 0;
+  return 2 * (int64_t)vol_host->H * vol_host->W * vol_host->zpitch;
+}
+
 extern "C" int so_render_train_forward(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host,
                                        const float* cam_mats, const float* pix, const so_ray_desc* rd,
                                        const so_render_params* pr, const float* jitter, const float* bkgd_rand,
                                        float* depth, float* acc, float* fars, float* rgb, float* sem, float* max_depth,
                                        float* weights, float* ts, float* deltas, float* eik_grad, float* sample_sdf,
-                                       float* workspace, void* stream) {
+                                       float* workspace, float* pair_workspace, void* stream) {
   bool want_rgb = rgb != nullptr, want_sem = sem != nullptr;
+  if (pair_workspace && (reinterpret_cast<uintptr_t>(pair_workspace) & 7)) return SO_ERR_INVALID_ARG;
   int rc = train_common_checks(vol_sdf, vol_feat, vol_host, cam_mats, rd, pr, workspace, want_rgb, want_sem, bkgd_rand);
   if (rc) return rc;
   RayDev R;
@@ -476,8 +760,29 @@ extern "C" int so_render_train_forward(const float* vol_sdf, const float* vol_fe
   ProfScope prof(6, st);
   const bool fast = V.ax[0].k1 == 0.f && V.ax[1].k1 == 0.f && V.ax[2].k1 == 0.f && (P.S & (P.S - 1)) == 0 && P.S >= 32 &&
                     P.cos_anneal == 1.0f && P.anchor_mid;
+  // batched-ray kernel (U chunks in flight, optional z-pair volume); the one-ray-per-warp kernel covers semantics,
+  // non-affine mappings, S not a multiple of 32 U and the cos-anneal phase
+  const bool v5 = fast && !want_sem && ((P.S >> 5) % SO_TRAIN_FWD5_U) == 0 && !g_force_fwd32;
 #define SO_TRAIN_FWD(RGB, SEM, F) render_train_fwd_kernel<RGB, SEM, F><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O)
-  if (want_sem) { if (fast) SO_TRAIN_FWD(true, true, true); else SO_TRAIN_FWD(true, true, false); }
+  if (v5) {
+    const float2* vp = nullptr;
+    if (pair_workspace) {
+      const long long nv = (long long)V.H * V.W * V.zpitch;
+      zpair_pack_kernel<<<(unsigned)ceil_div64(nv, 256), 256, 0, st>>>(vol_sdf, reinterpret_cast<float2*>(pair_workspace), nv, V.zpitch);
+      note_launch(1);
+      vp = reinterpret_cast<const float2*>(pair_workspace);
+    }
+    const long long n_batches = ceil_div64(R.ray_count, SO_TRAIN_FWD5_BATCH);
+    const unsigned grid5 = (unsigned)ceil_div64(n_batches, SO_TRAIN_FWD5_WARPS);   // one batch per warp
+    const bool cp = SO_TRAIN_FWD5_CONST_PITCH && V.zpitch == 32 && V.W == 257;
+#define SO_TRAIN_FWD5(RGB, PAIR, ZP, WZP) \
+  render_train_fwd5_kernel<RGB, PAIR, ZP, WZP><<<grid5, 32 * SO_TRAIN_FWD5_WARPS, 0, st>>>(V, R, P, workspace, vp, bkgd_rand, O)
+#define SO_TRAIN_FWD5_P(RGB, PAIR) do { if (cp) SO_TRAIN_FWD5(RGB, PAIR, 32, 257 * 32); else SO_TRAIN_FWD5(RGB, PAIR, 0, 0); } while (0)
+    if (want_rgb) { if (vp) SO_TRAIN_FWD5_P(true, true); else SO_TRAIN_FWD5_P(true, false); }
+    else { if (vp) SO_TRAIN_FWD5_P(false, true); else SO_TRAIN_FWD5_P(false, false); }
+#undef SO_TRAIN_FWD5_P
+#undef SO_TRAIN_FWD5
+  } else if (want_sem) { if (fast) SO_TRAIN_FWD(true, true, true); else SO_TRAIN_FWD(true, true, false); }
   else if (want_rgb) { if (fast) SO_TRAIN_FWD(true, false, true); else SO_TRAIN_FWD(true, false, false); }
   else { if (fast) SO_TRAIN_FWD(false, false, true); else SO_TRAIN_FWD(false, false, false); }
 #undef SO_TRAIN_FWD

@@ -258,11 +258,13 @@ class RenderTrainFunction(torch.autograd.Function):
         want = set(cfg['want'])
         out = {k: (torch.empty(shapes[k], device=dev) if k in want else None) for k in RenderTrainFunction.ORDER}
         ws = _render_ws(lib, rays, dev)
+        # scratch for the z-pair copy of the sdf volume (cfg['zpair']=False: gather from the volume itself)
+        pair = torch.empty(lib.so_render_train_pair_floats(C.byref(desc)), device=dev) if cfg.get('zpair', True) else None
         g = lambda k: _p(out[k])
         _lib.check(lib.so_render_train_forward(
             _p(vol_sdf), _p(vol_feat), C.byref(desc), _p(cam_mats), _p(pix), C.byref(rays), C.byref(params), _p(jitter), _p(bkgd),
             g('depth'), g('acc'), g('fars'), g('rgb'), g('sem'), g('max_depth'), g('weights'), g('ts'), g('deltas'),
-            g('eik_grad'), g('sample_sdf'), _p(ws), _stream()), 'so_render_train_forward')
+            g('eik_grad'), g('sample_sdf'), _p(ws), _p(pair), _stream()), 'so_render_train_forward')
         ctx.cfg = cfg
         ctx.save_for_backward(vol_sdf, vol_feat if vol_feat is not None else vol_sdf.new_empty(0))
         ctx.has_feat = vol_feat is not None

@@ -455,10 +455,12 @@ def _whole(views, split):
     base = getattr(views[0], '_base', None)
     if base is None or base.dim() != 3 or base.shape[1] != sum(split) or not base.is_contiguous():
         return None
+    if base.shape[0] != 1 or len(views) != len(split):
+        return None
     off = 0
     for v, n in zip(views, split):
-        if v._base is not base or v.shape[1] != n or v.data_ptr() != base.data_ptr() + off * base.shape[2] * base.element_size() \
-                or base.shape[0] != 1:
+        if v._base is not base or v.shape != (1, n, base.shape[2]) or v.stride() != base.stride() \
+                or v.data_ptr() != base.data_ptr() + off * base.shape[2] * base.element_size():
             return None
         off += n
     return base

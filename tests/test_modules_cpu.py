@@ -120,3 +120,19 @@ def test_modules_build_from_the_reference_config_dicts():
         if c['head'].get('return_second_grad'):
             with pytest.raises(NotImplementedError, match='second_grad'):
                 head.forward(representation=None, metas=None)
+
+
+def test_layer_token_buffer_detection():
+    """TPVFormerLayer keeps the three planes as torch.split views of one [1, Q, C] buffer; `_whole` must recognise exactly
+    that situation (and nothing else), otherwise the layer falls back to torch.cat like the reference."""
+    from selfocc_b200.encoder import _whole
+    split = [6, 2, 3]
+    buf = torch.randn(1, 11, 4)
+    views = torch.split(buf, split, 1)
+    assert _whole(views, split) is buf
+    assert _whole([v.clone() for v in views], split) is None                     # independent tensors
+    assert _whole(torch.split(torch.randn(2, 11, 4), split, 1), split) is None   # batch > 1 is not one contiguous token range
+    assert _whole(torch.split(buf, [3, 5, 3], 1), split) is None                 # other split
+    assert _whole((views[1], views[0], views[2]), split) is None                 # other order
+    wide = torch.randn(1, 11, 8)
+    assert _whole(torch.split(wide[..., :4], split, 1), split) is None           # column slice of a wider buffer

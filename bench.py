@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--workload', default='nuscenes_novel_depth_900x1600', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-train-probe', action='store_true', help='skip the training-form render forward side figure')
     return ap.parse_args()
 
 
@@ -261,6 +262,11 @@ def run_b200(args):
                        'l2_flush_between_steps': True},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'kernel_ms_per_step': breakdown}
+    if world == 1 and not args.no_train_probe:
+        try:
+            line['roofline_train_form'] = train_form_probe(dev, hbm_peak)
+        except Exception as e:                 # a side figure must never cost the bench line
+            line['roofline_train_form'] = {'error': repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_reference(args.workload, steps=2, warmup=1)
     print(json.dumps(line))
@@ -269,6 +275,47 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
+def train_form_probe(dev, hbm_peak, iters=10):
+    """North-star side figure (SURVEY 8d caveat): the TRAINING-form render forward -- the kernel that must emit ~6 KB of
+    per-sample tensors per ray -- at BASELINE configs[4] sizes (6 cams x 48 x 100 rays x 256 samples, TPV 257x257x25,
+    Cf = 1), timed with the library's CUDA events (L2 flushed before every launch), against the measured HBM peak.
+    Same set-up as scripts/bench_train_render.py.  Untimed w.r.t. the bench step; reported next to `roofline`."""
+    from selfocc_b200 import ops, synth, _lib
+    from selfocc_b200.mapping import GridMeterMapping
+    margs = dict(synth.NUSC_MAPPING, d_size=[24, 0], d_range=[-4.0, 4.0, 4.0])
+    aabb = [-51.2, -51.2, -4.0, 51.2, 51.2, 4.0]
+    m = GridMeterMapping(**margs)
+    desc = m.volume_desc(0)
+    vs = synth.pack_sdf_volume(synth.analytic_sdf_volume(m, noise=0.02), desc.zpitch).to(dev)
+    _, i2l = synth.camera_rig()
+    i2l = torch.tensor(i2l, dtype=torch.float32, device=dev)
+    ny, nx, S = 48, 100, 256
+    n = 6 * ny * nx
+    jit = torch.rand(n, S + 1, device=dev)
+    invs = torch.tensor([20.0], device=dev)
+    want = ['depth', 'acc', 'fars', 'weights', 'ts', 'deltas', 'eik_grad']
+    cfg = dict(desc=desc, cam_mats=i2l, rays=ops.make_ray_desc(6, grid=(ny, nx, 16.0, 3.0, 16.0, 5.0)),
+               params=ops.make_render_params(aabb, S, 20.0, training=True, bkgd='white'), jitter=jit, bkgd_rand=None, want=want)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _lib.profile_enable(True)
+    with torch.no_grad():
+        for it in range(iters + 3):
+            if it == 3:
+                torch.cuda.synchronize()
+                _lib.profile_reset()
+            flush.zero_()
+            ops.RenderTrainFunction.apply(vs, None, invs, cfg)
+    torch.cuda.synchronize()
+    ms, calls = _lib.profile_read()['render_train_fwd']
+    fwd_ms = ms / calls
+    out_bytes = n * (S * (4 + 4 + 4 + 12) + 4 * 3)
+    in_bytes = n * (S + 1) * 4 + desc.H * desc.W * desc.zpitch * 4
+    gbs = (out_bytes + in_bytes) / (fwd_ms * 1e-3) / 1e9
+    return {'kernel': 'render_train_fwd5_kernel (+ zpair_pack_kernel)', 'workload': 'nuscenes_occ_train 6x48x100 rays x256, Cf=1',
+            'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'launch_ms': fwd_ms,
+            'algorithmic_bytes_per_launch': out_bytes + in_bytes, 'rays_per_s': n / (fwd_ms * 1e-3)}
+
+
 def cpu_reference(workload, steps, warmup, full=False):
     """The reference's CPU PyTorch path = the oracle port (the reference itself cannot be installed: mmcv / sdfstudio fork
     absent).  Bounded sample, linearly extrapolated to the frame:

@@ -26,8 +26,9 @@ class FramePipeline:
         self.k = 0
 
     def _upload(self, slot, host):
-        if self.bufs[slot] is None:   # allocated once, on the caller's stream
-            self.bufs[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host]
+        if self.bufs[slot] is None:   # allocated once, on the caller's stream: the block may be recycled memory that work
+            self.bufs[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host]   # already queued there
+            self.h2d.wait_stream(self.cuda.current_stream(self.device))                                # still reads
         with self.cuda.stream(self.h2d):
             if self.free[slot] is not None:
                 self.h2d.wait_event(self.free[slot])

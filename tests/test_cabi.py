@@ -69,3 +69,31 @@ def test_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.so_tpv_decode(one, one, one, 48, one, one, one, one, C.byref(d), one, N, N) == -1   # invalid volume desc
     assert lib.so_error_string(-2) == b'unsupported configuration'
     assert lib.so_render_workspace_floats(0) == 2 and lib.so_render_workspace_floats(24) == 48
+
+
+def test_product_never_imports_the_oracle_or_reads_the_reference():
+    """The oracle is test infrastructure: only tests/, smoke() and bench.py's CPU legs may touch it, and nothing that
+    ships may read /root/reference at run time."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'selfocc_b200')
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(('.py', '.cu', '.cuh', '.h')):
+                continue
+            text = open(os.path.join(dirpath, f), errors='ignore').read()
+            if re.search(r'^\s*(from|import)\s+oracle\b', text, re.M) or '/root/reference' in text:
+                bad.append(os.path.relpath(os.path.join(dirpath, f), root))
+    assert not bad, bad
+    for f in ('bench.py', '__graft_entry__.py'):
+        assert '/root/reference' not in open(os.path.join(root, f)).read(), f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: a missing libselfocc_b200.so is an error at the first op, not a slower path."""
+    from selfocc_b200 import _lib
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    monkeypatch.setattr(_lib, '_lib', None)
+    with pytest.raises(_lib.SelfOccLibraryError):
+        _lib.load()

@@ -303,6 +303,10 @@ def run_b200(args):
             line['roofline_train_form'] = {'error': repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_reference(args.workload, steps=2, warmup=1)
+        try:                                   # same CPU leg: the oracle as checker on the bench workload ("AbsRel vs reference")
+            line['parity'] = parity_probe(model, feats_d, metas_d, args.workload, dev)
+        except Exception as e:
+            line['parity'] = {'error': repr(e)[:300]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -348,6 +352,52 @@ def train_form_probe(dev, hbm_peak, iters=10):
     return {'kernel': 'render_train_fwd5_kernel (+ zpair_pack_kernel)', 'workload': 'nuscenes_occ_train 6x48x100 rays x256, Cf=1',
             'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'launch_ms': fwd_ms,
             'algorithmic_bytes_per_launch': out_bytes + in_bytes, 'rays_per_s': n / (fwd_ms * 1e-3)}
+
+
+def parity_probe(model, feats, metas, workload, dev, stride=20):
+    """CPU leg, the oracle as the CHECKER (never the thing measured): "AbsRel vs reference" of BASELINE's metric on the
+    bench workload itself.  The bench model's own TPV planes and MLP go through the fp64 oracle (decode + render) on a strided
+    sub-grid of the frame (every `stride`-th pixel of all 6 cameras); the same sub-grid is rendered by the CUDA kernels from the
+    decoded volume the timed steps used.  Depth metric = utils/metric_util.py:247-265 (pred clamped to [1e-3, 80])."""
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender, rays as orays, metric
+    from selfocc_b200 import ops, synth
+    import numpy as np
+    w = WORKLOADS[workload]
+    head = model.head
+    f = head.model.field
+    with torch.no_grad():
+        r = model.lifter(ms_img_feats=feats)
+        r = model.encoder(representation=r['representation'], ms_img_feats=feats, metas=metas)
+        planes = r['representation']
+        head.prepare(representation=planes, metas=metas)
+        ny, nx = max(w['ray_number'][0] // stride, 1), max(w['ray_number'][1] // stride, 1)
+        H_img, W_img = w['ray_img_size']
+        M = head.img2lidar.matrices(metas, dev)[0].contiguous()
+        rd = ops.make_ray_desc(M.shape[0], grid=(ny, nx, W_img / nx, 0.0, H_img / ny, 0.0))
+        got = ops.render_infer(f.vol_sdf, f.vol_feat, f.desc, M, rd, head._params(False), want=('depth', 'max_idx', 'acc'))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    torch.set_num_threads(os.cpu_count())
+    mref = GridMeterMappingRef(**synth.NUSC_MAPPING)
+    l1, l2 = f.density_net[1], f.density_net[3]
+    cpu64 = lambda t: t.detach().cpu().double()
+    vol = orender.tpv_decode_ref(cpu64(planes[0][0]), cpu64(planes[1][0]), cpu64(planes[2][0]),
+                                 (mref.size_h, mref.size_w, mref.size_d), cpu64(l1.weight), cpu64(l1.bias), cpu64(l2.weight), cpu64(l2.bias))
+    pix = orays.fixed_ray_grid([ny, nx], [H_img, W_img])
+    i2l = torch.tensor(np.asarray(metas[0]['img2lidar']), dtype=torch.float32) if not torch.is_tensor(metas[0]['img2lidar']) \
+        else metas[0]['img2lidar'].detach().cpu().float()
+    origin, direction = orays.img2lidar_rays(i2l[None], pix)
+    ref = orender.head_render_ref(vol, mref, origin.double(), direction.double(), list(head.aabb), head._inv_s(), S=head.num_samples)
+    d, dref = got['depth'].cpu().double().reshape(-1), ref['depth'].reshape(-1)
+    rel = ((d - dref).abs() / dref.abs().clamp_min(1e-6)).max().item()
+    m = metric.cal_depth_metric_ref(d, dref.clamp(1e-3, 80))
+    idx_equal = (got['max_idx'].cpu().reshape(-1) == ref['max_idx'].reshape(-1)).float().mean().item()
+    return {'rays_checked': int(d.numel()), 'sub_grid': 'every %dth pixel of %d cameras' % (stride, M.shape[0]),
+            'oracle': 'fp64 CPU restatement (decode + render) on the bench model\'s own planes and MLP',
+            'depth_max_rel_err': rel, 'abs_rel': float(m['abs_rel']), 'rmse': float(m['rmse']), 'a1': float(m['a1']),
+            'max_depth_index_equal_frac': idx_equal, 'acc_max_abs_err': (got['acc'].cpu().double().reshape(-1) - ref['acc'].reshape(-1)).abs().max().item(),
+            'tolerance': 'depth 1e-4 relative (north star), indices equal except rounding-level ties', 'oracle_seconds': time.perf_counter() - t0}
 
 
 def cpu_reference(workload, steps, warmup, full=False):

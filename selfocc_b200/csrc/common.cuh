@@ -84,6 +84,8 @@ inline VolumeDev make_volume(const so_volume_desc& d, const float* sdf, const fl
 inline int validate_volume(const so_volume_desc* d) {
   if (!d) return SO_ERR_INVALID_ARG;
   if (d->H < 1 || d->W < 1 || d->Z < 1 || d->zpitch < d->Z) return SO_ERR_INVALID_ARG;
+  // the gather kernels index the sdf volume with 32-bit offsets
+  if ((int64_t)d->H * d->W * d->zpitch >= (int64_t)1 << 31) return SO_ERR_UNSUPPORTED;
   if (d->n_feat < 0 || (d->n_feat > 0 && (d->feat_pitch < d->n_feat || d->feat_pitch % 4))) return SO_ERR_INVALID_ARG;
   for (int i = 0; i < 3; ++i)
     if (!(d->axis[i].range0 > 0.f) || !(d->axis[i].size0 > 0.f)) return SO_ERR_INVALID_ARG;

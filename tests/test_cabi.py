@@ -67,6 +67,20 @@ def test_entry_points_reject_bad_arguments_without_a_gpu():
     d.H, d.W, d.Z, d.zpitch = 4, 4, 4, 2            # zpitch < Z
     assert lib.so_field_query(one, N, C.byref(d), one, 1, one, N, N, N) == -1
     assert lib.so_tpv_decode(one, one, one, 48, one, one, one, one, C.byref(d), one, N, N) == -1   # invalid volume desc
+    big = _lib.VolumeDesc()
+    big.H, big.W, big.Z, big.zpitch = 40000, 40000, 2, 8          # > 2^31 sdf entries: the kernels index with 32 bits
+    for i in range(3):
+        big.axis[i].range0, big.axis[i].size0 = 1.0, 1.0
+    assert lib.so_field_query(one, N, C.byref(big), one, 1, one, N, N, N) == -2
+    assert lib.so_render_train_pair_floats(C.byref(big)) == 0 and lib.so_render_train_pair_floats(None) == 0
+    ok = _lib.VolumeDesc()
+    ok.H, ok.W, ok.Z, ok.zpitch = 257, 257, 31, 32
+    for i in range(3):
+        ok.axis[i].range0, ok.axis[i].size0 = 51.2, 128.0
+    assert lib.so_render_train_pair_floats(C.byref(ok)) == 2 * 257 * 257 * 32
+    # training forward: a mis-aligned pair scratch is refused before any launch
+    assert lib.so_render_train_forward(one, N, C.byref(ok), one, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, one,
+                                       C.c_void_p(20), N) == -1
     assert lib.so_error_string(-2) == b'unsupported configuration'
     assert lib.so_render_workspace_floats(0) == 2 and lib.so_render_workspace_floats(24) == 48
 

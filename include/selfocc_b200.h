@@ -28,7 +28,7 @@ extern "C" {
 #define SO_ERR_CUDA (-3)          /* a CUDA runtime call or launch failed; see so_last_cuda_error */
 #define SO_ERR_NO_DEVICE (-4)
 
-#define SO_ABI_VERSION 2   /* 2: so_render_train_forward gained pair_workspace */
+#define SO_ABI_VERSION 3   /* 2: so_render_train_forward gained pair_workspace; 3: packed render volume entry points */
 
 /* ABI version of the loaded library (compare with SO_ABI_VERSION). */
 int so_abi_version(void);
@@ -135,6 +135,29 @@ int so_render_infer(const float* vol_sdf, const float* vol_feat, const so_volume
                     const so_render_params* params_host, const float* bkgd_rand,
                     float* depth, float* max_depth, int64_t* max_idx, float* acc,
                     float* normal_vis, float* rgb, float* sem, float* workspace, void* stream);
+
+/* Packed render volume: a once-per-frame repack of the decoded volume into the layout the gather of the inference
+ * render wants (built by NeuSHead.prepare, reused by every render of the frame -- eval_novel_depth.py:143-172 renders
+ * several poses per prepare):
+ *   n_feat == 0 : float2 [H][W][zpitch] {sdf[z], sdf[z+1]}  -- the 8 trilinear taps become 4 aligned 64-bit loads
+ *   n_feat == 3 : float4 [H][W][Z]      {r, g, b, sdf}       -- 8 aligned 128-bit loads fetch sdf and colour together
+ * so_render_pack_floats: floats needed (0: this channel count has no packed form).  pack must be 16-byte aligned. */
+int64_t so_render_pack_floats(const so_volume_desc* vol_host);
+int so_render_pack(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host, float* pack, void* stream);
+
+/* so_render_infer on the packed volume (same outputs, same semantics; `pack` from so_render_pack, NULL = plain
+ * so_render_infer).  Used when the metre->grid map is affine, num_samples is a power of two, the cos-anneal is finished,
+ * samples are taken at bin midpoints and no semantics are rendered; any other configuration is routed to so_render_infer.
+ * Rays that leave the volume take the zero-padding loop inside the same launch.  A warp stops marching when every
+ * ray's transmittance is below 1e-9 (changes the outputs by < 1e-9 relative, never the max-depth index).
+ * dbg_grid: optional probe [n, S, 3]: the fp32 (h, w, d) grid coordinates of every sample exactly as the kernel computed
+ * them (test hook: lets a fp64 oracle be evaluated in the kernel's own cells, the analytic sdf gradient being
+ * discontinuous across cell faces); NULL in production. */
+int so_render_infer_packed(const float* vol_sdf, const float* vol_feat, const so_volume_desc* vol_host, const float* pack,
+                           const float* cam_mats, const float* pix, const so_ray_desc* rays_host,
+                           const so_render_params* params_host, const float* bkgd_rand,
+                           float* depth, float* max_depth, int64_t* max_idx, float* acc,
+                           float* normal_vis, float* rgb, float* sem, float* workspace, float* dbg_grid, void* stream);
 
 /* B6-B10, B13  training-form render (NeuSHead.forward, neus_head.py:513-587): same sampling / field / alpha /
  * compositing as so_render_infer but it EMITS the per-sample tensors the losses consume (:667-682) and has a

@@ -60,14 +60,17 @@ def field_query_ref(vol, mapping, x, with_grad=True):
     return h.detach(), grad
 
 
-def field_query_manual(vol, mapping, x):
+def field_query_manual(vol, mapping, x, grid_override=None):
     """Same function as ``field_query_ref`` written as explicit 8-corner gathers so that BOTH outputs (values and
     the analytic position-gradient) are differentiable w.r.t. ``vol`` -- PyTorch has no double backward for
     ``grid_sampler_3d`` (the fork vendors ``cuda_gridsample_grad2`` for that, docs/installation.md:30).  Used by the
     training-parity tests; checked against ``field_query_ref`` in tests/test_oracle_selfcheck.py."""
     Cf, H, W, Z = vol.shape
     x = x.to(vol.dtype)
-    g = mapping.meter2grid(x, False)
+    # grid_override [N,3] (h, w, d): evaluate the interpolant at THESE grid coordinates (e.g. the fp32 coordinates a kernel
+    # used, exactly representable in fp64) while the metre->grid slopes still come from x -- separates "same function"
+    # from "same cell" when a sample sits within rounding of a cell face (the analytic gradient jumps there)
+    g = mapping.meter2grid(x, False) if grid_override is None else grid_override.to(vol.dtype)
     gh, gw, gd = g[:, 0], g[:, 1], g[:, 2]
     h0, w0, z0 = gh.floor(), gw.floor(), gd.floor()
     fh, fw, fz = gh - h0, gw - w0, gd - z0
@@ -129,7 +132,7 @@ def uniform_bins(nears, fars, S, jitter=None):
 
 def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=0.0, training=False,
                       jitter=None, cos_anneal=1.0, color_dims=0, sh_act='relu', bkgd='white',
-                      bkgd_rand=None, anchor='mid', differentiable=False):
+                      bkgd_rand=None, anchor='mid', differentiable=False, grid_override=None):
     """One ``self.model(ray_bundle)`` call of the reference (neus_head.py:353/394/531) for a chunk
     of rays o,d [R,3] (d unit), dnorm [R,1].  Returns the dict the head consumes."""
     R = o.shape[0]
@@ -139,7 +142,10 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
     deltas = ends - starts
     tq = mids if anchor == 'mid' else starts
     x = o[:, None, :] + d[:, None, :] * tq[..., None]
-    if differentiable:
+    grid = mapping.meter2grid(x.detach(), False)               # [R,S,3] (h, w, d) unnormalised grid coordinates of the samples
+    if grid_override is not None:
+        h, grad = field_query_manual(vol, mapping, x.reshape(-1, 3), grid_override.reshape(-1, 3))
+    elif differentiable:
         h, grad = field_query_manual(vol, mapping, x.reshape(-1, 3))
     else:
         h, grad = field_query_ref(vol, mapping, x.reshape(-1, 3))
@@ -165,7 +171,7 @@ def neus_render_chunk(vol, mapping, o, d, dnorm, aabb, inv_s, S=256, near_plane=
     normal = (weights[..., None] * normals).sum(-2)
     out = dict(depth=depth, accumulation=acc, weights=weights, starts=starts, ends=ends, sdf=sdf,
                eik_grad=grad, normal=normal, normal_vis=(normal + 1.0) / 2.0, nears=nears,
-               fars=fars / dnorm[:, 0], alpha=alpha)
+               fars=fars / dnorm[:, 0], alpha=alpha, grid=grid)
     if color_dims > 0:
         raw = h[..., 1:4] * C0  # SH degree 0 (sh_render.py:84-94)
         rgb_s = torch.relu(raw + 0.5) if sh_act == 'relu' else torch.sigmoid(raw)
@@ -198,15 +204,16 @@ def max_depth_ref(weights, ts, deltas):
     return torch.gather(ts, -1, idx).squeeze(-1), idx.squeeze(-1)
 
 
-def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, max_depth_on_cpu=False, **kw):
+def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, max_depth_on_cpu=False, grid_override=None, **kw):
     """NeuSHead.render (neus_head.py:308-471) after ray generation: origin [1,N,3], direction
     [1,N,R,3] un-normalised.  Serial chunk loop with ``torch.chunk`` sizes when batch > 0."""
     from .rays import flatten_rays, num_chunks
     bs, n_cam, n_ray = direction.shape[:3]
     o, d, nrm = flatten_rays(origin, direction)
     n = num_chunks(o.shape[0], batch)
-    outs = [neus_render_chunk(vol, mapping, oc, dc, nc, aabb, inv_s, **kw)
-            for oc, dc, nc in zip(torch.chunk(o, n), torch.chunk(d, n), torch.chunk(nrm, n))]
+    go = [None] * n if grid_override is None else torch.chunk(grid_override.reshape(o.shape[0], -1, 3), n)
+    outs = [neus_render_chunk(vol, mapping, oc, dc, nc, aabb, inv_s, grid_override=gc, **kw)
+            for oc, dc, nc, gc in zip(torch.chunk(o, n), torch.chunk(d, n), torch.chunk(nrm, n), go)]
     cat = lambda k: torch.cat([c[k] for c in outs])
     weights = cat('weights')
     ts = (cat('starts') + cat('ends')) / 2 / nrm
@@ -222,7 +229,7 @@ def head_render_ref(vol, mapping, origin, direction, aabb, inv_s, batch=0, max_d
                 max_depth=max_depth.reshape(shp), max_idx=max_idx.reshape(shp),
                 weights=weights.reshape(*shp, -1), ts=ts.reshape(*shp, -1), deltas=deltas.reshape(*shp, -1),
                 sdf=cat('sdf').reshape(*shp, -1), eik_grad=cat('eik_grad').reshape(*shp, -1, 3),
-                fars=cat('fars').reshape(shp),
+                fars=cat('fars').reshape(shp), grid=cat('grid').reshape(*shp, -1, 3),
                 sem=cat('sem').reshape(*shp, -1) if 'sem' in outs[0] else None)
 
 

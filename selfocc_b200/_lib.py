@@ -8,7 +8,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SELFOCC_B200_LIB') or os.path.join(_PKG, 'lib', 'libselfocc_b200.so')   # env: experimental variant
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class AxisMap(C.Structure):
@@ -53,6 +53,10 @@ SIGNATURES = {
     'so_render_workspace_floats': (C.c_int64, [_L]),
     'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'so_render_pack_floats': (_L, [C.POINTER(VolumeDesc)]),
+    'so_render_pack': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P]),
+    'so_render_infer_packed': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
+                                         _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'so_render_train_forward': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                           _P, _P] + [_P] * 11 + [_P, _P, _P]),
     'so_render_train_pair_floats': (_L, [C.POINTER(VolumeDesc)]),

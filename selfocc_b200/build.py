@@ -7,9 +7,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB = os.path.join(LIB_DIR, 'libselfocc_b200.so')
-SOURCES = ['abi.cu', 'render.cu', 'render_train.cu', 'decode.cu', 'msda.cu', 'gemm.cu', 'norm.cu']
+SOURCES = ['abi.cu', 'render.cu', 'render_fast.cu', 'render_train.cu', 'decode.cu', 'msda.cu', 'gemm.cu', 'norm.cu']
 # approx-unit math (ex2/rcp/rsq) without the denormal range-scaling wrappers: ~20 instructions per render sample
-PER_SOURCE_FLAGS = {'render.cu': ['-ftz=true'], 'render_train.cu': ['-ftz=true'], 'msda.cu': ['-ftz=true'], 'decode.cu': ['-ftz=true']}
+PER_SOURCE_FLAGS = {'render.cu': ['-ftz=true'], 'render_fast.cu': ['-ftz=true'], 'render_train.cu': ['-ftz=true'], 'msda.cu': ['-ftz=true'], 'decode.cu': ['-ftz=true']}
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -38,7 +38,10 @@ def build(force=False, verbose=False, out=None, defines=()):
     tag = '' if out is None else '.' + os.path.splitext(os.path.basename(out))[0]
     objs = []
     procs = []
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = list(SOURCES)
+    missing = [s for s in srcs if not os.path.exists(os.path.join(CSRC, s))]
+    if missing:
+        raise RuntimeError('CUDA sources missing from %s: %s' % (CSRC, missing))
     for s in srcs:
         o = os.path.join(LIB_DIR, s.replace('.cu', tag + '.o'))
         objs.append(o)

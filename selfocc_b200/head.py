@@ -143,6 +143,7 @@ class _SDFField(nn.Module):
         self.deviation_network = _Deviation(beta_init)
         self.desc = self.mapping.volume_desc(color_dims)
         self.vol_sdf = self.vol_feat = None
+        self._pack = None
 
     def pre_compute_density_color(self, representation):
         hw, zh, wz = representation
@@ -150,6 +151,17 @@ class _SDFField(nn.Module):
         l1, l2 = self.density_net[1], self.density_net[3]
         self.vol_sdf, self.vol_feat = ops.tpv_decode(hw[0].contiguous(), zh[0].contiguous(), wz[0].contiguous(),
                                                      l1.weight, l1.bias, l2.weight, l2.bias, self.desc)
+        self._pack = None
+
+    def render_pack(self):
+        """The frame's packed render volume (ops.render_pack), built on the first render after a decode and reused by
+        every further render of the frame (eval_novel_depth.py:143-172: one prepare, several poses).  Keyed on the
+        volume tensors' identity and version, so a volume swapped in from outside (training forward, tests) is repacked."""
+        vf = self.vol_feat
+        key = (self.vol_sdf.data_ptr(), self.vol_sdf._version, None if vf is None else (vf.data_ptr(), vf._version))
+        if self._pack is None or self._pack[0] != key:
+            self._pack = (key, ops.render_pack(self.vol_sdf, vf, self.desc))    # None: no packed form for this channel count
+        return self._pack[1]
 
     def forward_geonetwork(self, xyz):
         s, _, f = ops.field_query(self.vol_sdf, self.vol_feat, self.desc, xyz.reshape(-1, 3).contiguous(), want_feat=True)
@@ -271,7 +283,8 @@ class NeuSHead(nn.Module):
             + (['rgb'] if has_rgb else []) + (['sem'] if self.return_sem else [])
         bk = torch.rand(count, 3, device=dev) if (self.render_bkgd == 'random' and has_rgb) else None
         out = ops.render_infer(f.vol_sdf, f.vol_feat, f.desc, M[0].contiguous(), rd, self._params(False),
-                               pix=None if grid is not None else rays.contiguous(), bkgd_rand=bk, want=want)
+                               pix=None if grid is not None else rays.contiguous(), bkgd_rand=bk, want=want,
+                               pack=f.render_pack())
         full = ray_range is None
         shp = (lambda t, *tail: t.reshape(bs, num_cams, num_rays, *tail)) if full else (lambda t, *tail: t)
         outputs = {'ms_depths': [shp(out['depth'])],

@@ -83,11 +83,27 @@ def make_render_params(aabb, num_samples, inv_s, near_plane=0.0, training=False,
     return p
 
 
-def render_infer(vol_sdf, vol_feat, desc, cam_mats, rays, params, pix=None, bkgd_rand=None, want=('depth',),
-                 out=None):
-    """Fused inference render.  ``want`` subset of depth,max_depth,max_idx,acc,normal_vis,rgb,sem.
-    Returns a dict of flat per-ray tensors for rays [ray_begin, ray_begin+ray_count)."""
+def render_pack(vol_sdf, vol_feat, desc):
+    """Once-per-frame repack of the decoded volume for the packed render kernels (so_render_pack): float2 z-pairs when no
+    colour is decoded, float4 (r, g, b, sdf) for color_dims == 3.  Returns None when this channel count has no packed form."""
     lib = _lib.load()
+    _chk(vol_sdf, name='vol_sdf'); _chk(vol_feat, name='vol_feat')
+    n = lib.so_render_pack_floats(C.byref(desc))
+    if n <= 0:
+        return None
+    pack = torch.empty(n, device=vol_sdf.device, dtype=torch.float32)
+    _lib.check(lib.so_render_pack(_p(vol_sdf), _p(vol_feat), C.byref(desc), _p(pack), _stream()), 'so_render_pack')
+    return pack
+
+
+def render_infer(vol_sdf, vol_feat, desc, cam_mats, rays, params, pix=None, bkgd_rand=None, want=('depth',),
+                 out=None, pack=None, probe_grid=False):
+    """Fused inference render.  ``want`` subset of depth,max_depth,max_idx,acc,normal_vis,rgb,sem.
+    Returns a dict of flat per-ray tensors for rays [ray_begin, ray_begin+ray_count).
+    ``pack`` = render_pack(...) selects the packed-volume kernels; ``probe_grid`` (tests) adds 'grid' [n, S, 3], the fp32
+    grid coordinates of every sample as the packed kernel computed them."""
+    lib = _lib.load()
+    _chk(pack, name='pack')
     _chk(vol_sdf, name='vol_sdf'); _chk(vol_feat, name='vol_feat'); _chk(cam_mats, name='cam_mats')
     _chk(pix, name='pix'); _chk(bkgd_rand, name='bkgd_rand')
     assert cam_mats.shape == (rays.n_cam, 4, 4)
@@ -106,9 +122,17 @@ def render_infer(vol_sdf, vol_feat, desc, cam_mats, rays, params, pix=None, bkgd
         else:
             res[k] = torch.empty(shapes[k][0], device=dev, dtype=shapes[k][1])
     g = lambda k: _p(res.get(k))
-    _lib.check(lib.so_render_infer(_p(vol_sdf), _p(vol_feat), C.byref(desc), _p(cam_mats), _p(pix), C.byref(rays),
-                                   C.byref(params), _p(bkgd_rand), g('depth'), g('max_depth'), g('max_idx'), g('acc'),
-                                   g('normal_vis'), g('rgb'), g('sem'), _p(ws), _stream()), 'so_render_infer')
+    if pack is None and not probe_grid:
+        _lib.check(lib.so_render_infer(_p(vol_sdf), _p(vol_feat), C.byref(desc), _p(cam_mats), _p(pix), C.byref(rays),
+                                       C.byref(params), _p(bkgd_rand), g('depth'), g('max_depth'), g('max_idx'), g('acc'),
+                                       g('normal_vis'), g('rgb'), g('sem'), _p(ws), _stream()), 'so_render_infer')
+        return res
+    if probe_grid:
+        res['grid'] = torch.empty(n, params.num_samples, 3, device=dev, dtype=torch.float32)
+    _lib.check(lib.so_render_infer_packed(_p(vol_sdf), _p(vol_feat), C.byref(desc), _p(pack), _p(cam_mats), _p(pix), C.byref(rays),
+                                          C.byref(params), _p(bkgd_rand), g('depth'), g('max_depth'), g('max_idx'), g('acc'),
+                                          g('normal_vis'), g('rgb'), g('sem'), _p(ws), g('grid'), _stream()),
+               'so_render_infer_packed')
     return res
 
 

@@ -145,6 +145,89 @@ def dump_reference_model_configs():
     print('wrote model configs of', sorted(out))
 
 
-if __name__ == '__main__':
+
+
+def bevnerf_golden():
+    """Pins oracle rows B5/B7 (TPV -> decoded volume, trilinear field query) to the reference's only in-tree statement of
+    them: model/head/nerfacc_head/bev_nerf.py:62-175 (``BEVNeRF``, tpv=True).  The module is executed UNMODIFIED; its two
+    non-torch imports are satisfied by (a) a 3-line stand-in for ``mmengine.model.BaseModule`` (an nn.Module that accepts
+    ``init_cfg``) and (b) a synthetic package tree so that its relative imports resolve to the reference's own
+    ``mappings.py`` / ``sh_render.py`` loaded by file path.  Writes tests/golden/reference_golden_bevnerf.npz."""
+    import types
+    import torch.nn as nn
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+    mm, mmm = types.ModuleType('mmengine'), types.ModuleType('mmengine.model')
+    mmm.BaseModule = BaseModule
+    mm.model = mmm
+    sys.modules.setdefault('mmengine', mm)
+    sys.modules.setdefault('mmengine.model', mmm)
+    for pkg in ('refpkg', 'refpkg.encoder', 'refpkg.encoder.bevformer', 'refpkg.head', 'refpkg.head.utils',
+                'refpkg.head.nerfacc_head'):
+        p = types.ModuleType(pkg)
+        p.__path__ = []
+        sys.modules[pkg] = p
+
+    def load_as(rel, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    load_as('model/encoder/bevformer/mappings.py', 'refpkg.encoder.bevformer.mappings')
+    load_as('model/head/utils/sh_render.py', 'refpkg.head.utils.sh_render')
+    bn = load_as('model/head/nerfacc_head/bev_nerf.py', 'refpkg.head.nerfacc_head.bev_nerf')
+
+    out = {}
+    cases = {
+        # name: (mapping args, embed dims, color dims, sem dims)
+        'a': (dict(nonlinear_mode='linear', h_size=[4, 0], h_range=[6.4, 0], h_half=False, w_size=[5, 0], w_range=[8.0, 0],
+                   w_half=False, d_size=[6, 0], d_range=[-2.0, 4.0, 4.0]), 32, 3, 5),
+        'b': (dict(nonlinear_mode='linear', h_size=[6, 0], h_range=[9.6, 0], h_half=True, w_size=[3, 0], w_range=[4.8, 0],
+                   w_half=False, d_size=[4, 0], d_range=[-1.0, 3.0, 3.0]), 16, 0, 0),
+    }
+    for name, (margs, C, cd, sd) in cases.items():
+        torch.manual_seed(7 if name == 'a' else 11)
+        net = bn.BEVNeRF(mapping_args=margs, embed_dims=C, color_dims=cd, sem_dims=sd, density_layers=2, sh_deg=0,
+                         sh_act='relu', tpv=True)
+        H, W, Z = net.h_size, net.w_size, net.z_size
+        planes = [0.5 * torch.randn(1, n, C) for n in (H * W, Z * H, W * Z)]
+        with torch.no_grad():
+            net.pre_compute_density_color(planes)
+            vol = net.density_color.clone()                       # [1, Cf, H, W, Z]
+            lo = torch.tensor([-margs['w_range'][0] * 1.2, (0.0 if margs['h_half'] else -margs['h_range'][0]) * 1.2 - 0.5,
+                               margs['d_range'][0] - 0.7])
+            hi = torch.tensor([margs['w_range'][0] * 1.2, margs['h_range'][0] * 1.2, margs['d_range'][1] + 0.7])
+            x = lo + (hi - lo) * torch.rand(257, 3)               # includes points outside the volume (zeros padding)
+            dirs = torch.nn.functional.normalize(torch.randn(x.shape[0], 3), dim=-1)   # SH degree 0 ignores them (sh_render.py:48)
+            rgb, sigma, sems = net(x, condition=dirs)
+            sigma_geo, sems_geo = net.forward_geo(x)
+            dens = net.query_density(x)
+        out[name + '_margs'] = np.array(json_dumps(margs))
+        out[name + '_dims'] = np.array([C, cd, sd, H, W, Z])
+        for i, p in enumerate(planes):
+            out['%s_plane%d' % (name, i)] = p.numpy()
+        out[name + '_w1'], out[name + '_b1'] = net.density_net[1].weight.detach().numpy(), net.density_net[1].bias.detach().numpy()
+        out[name + '_w2'], out[name + '_b2'] = net.density_net[3].weight.detach().numpy(), net.density_net[3].bias.detach().numpy()
+        out[name + '_vol'] = vol.numpy()
+        out[name + '_x'] = x.numpy()
+        out[name + '_rgb'], out[name + '_sigma'], out[name + '_sems'] = rgb.numpy(), sigma.numpy(), sems.numpy()
+        out[name + '_sigma_geo'], out[name + '_sems_geo'], out[name + '_dens'] = sigma_geo.numpy(), sems_geo.numpy(), dens.numpy()
+    np.savez_compressed(os.path.join(HERE, 'reference_golden_bevnerf.npz'), **out)
+    print('wrote bevnerf golden:', len(out), 'arrays')
+
+
+def json_dumps(o):
+    import json
+    return json.dumps(o, sort_keys=True)
+
+
+if __name__ == '__main__' and '--bevnerf' in sys.argv:
+    bevnerf_golden()
+
+if __name__ == '__main__' and '--bevnerf' not in sys.argv:
     main()
     dump_reference_model_configs()
+    bevnerf_golden()

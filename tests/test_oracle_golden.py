@@ -1,6 +1,7 @@
 """Pin the oracle against golden vectors produced by the reference's own importable code
 (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 from oracle.mapping import GridMeterMappingRef
 from oracle import lifting, rays, render, metric
@@ -71,3 +72,39 @@ def test_ref3d_tables_shapes():
     assert hw.shape == (8, 257 * 257, 3) and zh.shape == (48, 31 * 257, 3) and wz.shape == (48, 257 * 31, 3)
     # pillar of the hw plane spans z in [-4, 5]
     assert torch.allclose(hw[:, 0, 2], torch.linspace(-4, 5, 8))
+
+
+# ---- B5 / B7 pinned to the reference's in-tree statement (BEVNeRF, bev_nerf.py:62-175) -----------------------------
+@pytest.mark.parametrize('case', ['a', 'b'])
+def test_decode_and_field_query_match_bevnerf(case):
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden_bevnerf.npz'))
+    margs = json.loads(str(g[case + '_margs']))
+    C, cd, sd, H, W, Z = (int(v) for v in g[case + '_dims'])
+    m = GridMeterMappingRef(**margs)
+    assert (m.size_h, m.size_w, m.size_d) == (H, W, Z)
+    planes = [T(g['%s_plane%d' % (case, i)])[0] for i in range(3)]
+    w1, b1, w2, b2 = (T(g[case + k]) for k in ('_w1', '_b1', '_w2', '_b2'))
+    ref_vol = T(g[case + '_vol'])[0]                                          # [Cf, H, W, Z] from pre_compute_density_color
+    # B5: same fp32 arithmetic (broadcast sum, Softplus, Linear); only the GEMM blocking differs -> a few ulp
+    vol = render.tpv_decode_ref(planes[0], planes[1], planes[2], (H, W, Z), w1, b1, w2, b2)
+    assert vol.shape == ref_vol.shape
+    assert torch.allclose(vol, ref_vol, rtol=0, atol=2e-6)
+    vol64 = render.tpv_decode_ref(*[p.double() for p in planes], (H, W, Z), w1.double(), b1.double(), w2.double(), b2.double())
+    assert (vol64 - ref_vol.double()).abs().max() < 5e-6
+    # B7: the oracle's field query on the REFERENCE's volume must reproduce BEVNeRF.forward / forward_geo / query_density
+    x = T(g[case + '_x'])
+    h, _ = render.field_query_ref(ref_vol, m, x, with_grad=False)
+    assert torch.allclose(torch.nn.functional.softplus(h[:, :1]), T(g[case + '_sigma']), rtol=0, atol=1e-6)
+    assert torch.equal(T(g[case + '_sigma']), T(g[case + '_sigma_geo'])) and torch.equal(T(g[case + '_sigma']), T(g[case + '_dens']))
+    if cd:
+        rgb = torch.relu(h[:, 1:4] * render.C0 + 0.5)                         # sh_render.py:84-94, degree 0
+        assert torch.allclose(rgb, T(g[case + '_rgb']), rtol=0, atol=1e-6)
+    if sd:
+        assert torch.allclose(torch.softmax(h[:, 1 + cd:], -1), T(g[case + '_sems']), rtol=0, atol=1e-6)
+    # the explicit 8-corner form used by the training-parity tests states the same function (incl. zeros padding outside)
+    hm, _ = render.field_query_manual(ref_vol.double(), m, x.double())
+    assert (hm - h.double()).abs().max() < 1e-5
+    outside = ((x[:, 0].abs() > margs['w_range'][0]) | (x[:, 2] > margs['d_range'][1] + 0.31)).sum()
+    assert outside > 10                                                       # the padding branch is exercised

@@ -196,6 +196,15 @@ int so_render_train_backward(const float* vol_sdf, const float* vol_feat, const 
 int so_field_query_backward(const so_volume_desc* vol_host, const float* points, int64_t n, const float* g_sdf,
                             const float* g_grad, const float* g_feat, float* g_vol_sdf, float* g_vol_feat, void* stream);
 
+/* B8  `second_grad` (neus_head.py:177,703-706 -> loss/second_grad_loss.py:19-20), DECLARED ASSUMPTION: the quantity lives in
+ * the un-vendored fork; restated as the double-backward idiom d(sum_j d sdf/d x_j)/d x of the trilinear field = the row
+ * sums of its Hessian in metres (pure second derivatives vanish inside a cell, the mixed ones do not).  points [n,3]
+ * metres -> second_grad [n,3].  Backward: g_second_grad [n,3] accumulated atomically into g_vol_sdf (caller zero-fills). */
+int so_field_second_grad(const float* vol_sdf, const so_volume_desc* vol_host, const float* points, int64_t n,
+                         float* second_grad, void* stream);
+int so_field_second_grad_backward(const so_volume_desc* vol_host, const float* points, int64_t n, const float* g_second_grad,
+                                  float* g_vol_sdf, void* stream);
+
 /* B12  field query at arbitrary points.  Replaces field.forward_sdfnetwork / forward_geonetwork
  * as used by NeuSHead.get_uniform_sdf (neus_head.py:265-293).  points [n,3] metres ->
  * sdf [n], grad [n,3] (NULL ok), feat [n, n_feat] raw decoded channels 1.. (NULL ok). */

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/selfocc_b200.h"
 
 namespace so {
@@ -20,6 +21,24 @@ inline int check_cuda(cudaError_t e) {
 inline int check_launch() { return check_cuda(cudaGetLastError()); }
 
 constexpr int kNumSMs = 148;  // B200
+
+// cudaFuncSetAttribute is PER DEVICE: a process-wide `static bool` would leave the second GPU of a multi-device process
+// without its opt-in shared-memory size.  One bit per device ordinal; setting the attribute twice is harmless, so the
+// check-then-set race between host threads is benign.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done{0};
+  template <typename F>
+  int run(F&& set_attr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SO_ERR_CUDA;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return SO_OK;
+    int rc = set_attr();
+    if (rc) return rc;
+    done.fetch_or(bit, std::memory_order_release);
+    return SO_OK;
+  }
+};
 
 // Device-time bracket around the dominant kernel of an entry point (no-op unless so_profile_enable(1)).
 void prof_begin(int tag, cudaStream_t st);

@@ -340,12 +340,11 @@ int launch_decode(const float* hw, const float* zh, const float* wz, const float
                   const float* b2, const so_volume_desc* d, float* vol_sdf, float* vol_feat, cudaStream_t st) {
   constexpr int LD = C + 4;
   size_t smem = sizeof(float) * ((size_t)kRows * LD + (size_t)C * LD + (size_t)kMaxOut * C + C + kMaxOut);
-  static bool attr_set = false;
-  if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(tpv_decode_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (rc) return rc;
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_simt;
+  int rc_attr = attr_simt.run([smem] {
+    return check_cuda(cudaFuncSetAttribute(tpv_decode_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
+  if (rc_attr) return rc_attr;
   dim3 grid((unsigned)ceil_div64((int64_t)d->W * d->Z, kRows), (unsigned)d->H);
   ProfScope prof(1, st);
   tpv_decode_kernel<C><<<grid, kThreads, smem, st>>>(hw, zh, wz, w1, b1, w2, b2, d->H, d->W, d->Z, d->zpitch,
@@ -381,13 +380,14 @@ extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const flo
     const int n_out = 1 + d->n_feat;
     DecSmem Ls = dec_smem(C, n_out);
     if (Ls.stages >= 2) {
-      static bool attr_tc = false;
-      if (!attr_tc) {
-        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
-        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
-        if ((rc = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
-        attr_tc = true;
-      }
+      static PerDeviceOnce attr_tc;
+      if ((rc = attr_tc.run([] {
+             int r;
+             if ((r = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return r;
+             if ((r = check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return r;
+             return check_cuda(cudaFuncSetAttribute(tpv_decode_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+           })))
+        return rc;
       const int tiles_per_row = (int)ceil_div64((int64_t)d->W * d->Z, kBM);
       const int n_tiles = tiles_per_row * d->H;
       const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;

@@ -440,11 +440,11 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
   if ((reinterpret_cast<uintptr_t>(y) & 15) || (N % 4)) return SO_ERR_UNSUPPORTED;   // TMA store: 16-byte aligned rows
   CUtensorMap my;
   if ((rc = make_tmap(&my, y, M, N, 32))) return rc;                                 // store box: 32 rows x 32 floats
-  static int smem_set = 0;
-  if (smem_set < cfg.smem) {
-    if ((rc = check_cuda(cudaFuncSetAttribute(linear_3xtf32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return rc;
-    smem_set = 227 * 1024;
-  }
+  static PerDeviceOnce smem_attr;
+  if ((rc = smem_attr.run([] {
+         return check_cuda(cudaFuncSetAttribute(linear_3xtf32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+       })))
+    return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = (int)ceil_div64(N, cfg.BN), m_tiles = (int)ceil_div64(M, kBM);
   int groups = kNumSMs / n_tiles;

@@ -449,6 +449,8 @@ extern "C" int so_tpv_cross_attn_forward_strided(const float* value, const int64
   if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !uv || !vis || !slots) return SO_ERR_INVALID_ARG;
   if (N < 1 || Nv < 1 || Hd < 1 || Q < 1 || L < 1 || D < 1) return SO_ERR_INVALID_ARG;
   if (value_ld < Hd * Dh || offsets_ld < Hd * L * D * 2 || logits_ld < Hd * L * D || (value_ld & 3)) return SO_ERR_INVALID_ARG;
+  // the kernels read value rows as float4 and (x, y) offsets as float2
+  if ((offsets_ld & 1) || (reinterpret_cast<uintptr_t>(offsets) & 7) || (reinterpret_cast<uintptr_t>(value) & 15)) return SO_ERR_INVALID_ARG;
   if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);
@@ -481,6 +483,7 @@ extern "C" int so_tpv_self_attn_forward_strided(const float* value, const int64_
   if (!value || !spatial_shapes || !level_start_index || !offsets || !logits || !ref || !out) return SO_ERR_INVALID_ARG;
   if (Nv < 1 || Hd < 1 || Q < 1 || L < 1 || P < 1) return SO_ERR_INVALID_ARG;
   if (value_ld < Hd * Dh || offsets_ld < Hd * L * P * 2 || logits_ld < Hd * L * P || (value_ld & 3)) return SO_ERR_INVALID_ARG;
+  if ((offsets_ld & 1) || (reinterpret_cast<uintptr_t>(offsets) & 7) || (reinterpret_cast<uintptr_t>(value) & 15)) return SO_ERR_INVALID_ARG;
   if (L > kMaxLevels) return SO_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const long long* shp = reinterpret_cast<const long long*>(spatial_shapes);

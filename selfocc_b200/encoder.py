@@ -141,7 +141,7 @@ def fast_linear(lin, x, relu=False, residual=None, out=None):
     """nn.Linear forward for the inference path: the tcgen05 split-precision GEMM (``so_linear_3xtf32``) when the shape
     allows it (K % 96 == 0), cuBLAS otherwise.  Split weights are cached per parameter version."""
     w = lin.weight
-    if x.is_cuda and x.dtype == torch.float32 and ops.linear_supported(w.shape[1]):
+    if x.is_cuda and x.dtype == torch.float32 and ops.linear_supported(w.shape[1], w.shape[0]):
         ver = (w._version, w.data_ptr())
         ent = getattr(lin, '_so_split', None)       # kept on the module itself: no aliasing between models
         if ent is None or ent[0] != ver:
@@ -181,7 +181,7 @@ def fast_linear_cat(owner, key, lins, x):
 
 
 def _fusable(lins, x):
-    return x.is_cuda and x.dtype == torch.float32 and all(ops.linear_supported(l.weight.shape[1]) for l in lins)
+    return x.is_cuda and x.dtype == torch.float32 and all(ops.linear_supported(l.weight.shape[1], l.weight.shape[0]) for l in lins)
 
 
 def _needs_grad(*tensors):

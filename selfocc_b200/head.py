@@ -200,7 +200,7 @@ class NeuSHead(nn.Module):
                  ray_x_dsr_max=None, ray_y_dsr_max=None, trans_kw='img2lidar', trans_kw_eval=None, novel_view=None,
                  render_bkgd='white', mapping_args=None, embed_dims=128, color_dims=0, density_layers=2, sh_deg=2,
                  sh_act='relu', init_cfg=None, print_freq=50, two_split=True, tpv=False, using_2d_img_feats=False,
-                 sample_anchor='mid', **kwargs):
+                 sample_anchor='mid', second_grad_assumption=None, **kwargs):
         super().__init__()
         given = dict(use_numerical_gradients=use_numerical_gradients, use_uniform_gradient=use_uniform_gradient,
                      calculate_online=calculate_online, beta_hand_tune=beta_hand_tune, estimate_flow=estimate_flow,
@@ -224,12 +224,41 @@ class NeuSHead(nn.Module):
         self.return_uniform_sdf, self.return_max_depth = return_uniform_sdf, return_max_depth
         self.return_surface_sdf, self.return_sample_sdf, self.return_sem = return_surface_sdf, return_sample_sdf, return_sem
         self.return_second_grad = return_second_grad
+        self.second_grad_assumption = (os.environ.get('SELFOCC_B200_SECOND_GRAD', '0') == '1') if second_grad_assumption is None \
+            else bool(second_grad_assumption)
         if return_sem and color_dims <= 3:
             raise ValueError('return_sem needs color_dims > 3 (3 rgb + semantic logits)')
         self.z_size = self.model.field.mapping.size_d
         self.bev_size = [self.model.field.mapping.size_h, self.model.field.mapping.size_w]
         self.two_split = two_split
         self.cos_anneal_ratio = 1.0
+
+    # ------------------------------------------------------------------ checkpoints
+    # The field's parameters follow the in-repo analogue's names (bev_nerf.py:62-71: ``density_net.{1,3}``) under
+    # ``model.field``; a checkpoint written by the un-vendored fork may keep them under another module path.  On load, a
+    # key of this head that is missing is looked up (i) through ``checkpoint_key_map`` ({regex: replacement}, applied to the
+    # key relative to the head) and (ii) by its unambiguous suffix anywhere under the head's prefix.
+    FIELD_SUFFIXES = ('density_net.1.weight', 'density_net.1.bias', 'density_net.3.weight', 'density_net.3.bias',
+                      'deviation_network.variance')
+    checkpoint_key_map = {}
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        import re
+        for k in [k for k in state_dict if k.startswith(prefix)]:
+            rel = k[len(prefix):]
+            for pat, rep in self.checkpoint_key_map.items():
+                new = re.sub(pat, rep, rel)
+                if new != rel and prefix + new not in state_dict:
+                    state_dict[prefix + new] = state_dict.pop(k)
+                    break
+        for suf in self.FIELD_SUFFIXES:
+            tgt = prefix + 'model.field.' + suf
+            if tgt in state_dict:
+                continue
+            cands = [k for k in state_dict if k.startswith(prefix) and k.endswith('.' + suf) and k != tgt]
+            if len(cands) == 1:
+                state_dict[tgt] = state_dict.pop(cands[0])
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     # ------------------------------------------------------------------ helpers
     def _sampler(self):
@@ -328,10 +357,12 @@ class NeuSHead(nn.Module):
 
     def forward(self, representation, metas=None, **kwargs):
         """neus_head.py:473-713 (training form: per-sample weights / ts / deltas / eik_grad)."""
-        if self.return_second_grad:
+        if self.return_second_grad and not self.second_grad_assumption:
             raise NotImplementedError(
                 "return_second_grad=True: the `second_grad` training output is computed inside the un-vendored sdfstudio fork "
-                "(cuda_gridsample_grad2, `use_compact_2nd_grad`) and its definition cannot be recovered from the reference; "
-                "set return_second_grad=False and drop SecondGradLoss to train, or use prepare()/render()/forward_occ()")
+                "(cuda_gridsample_grad2, `use_compact_2nd_grad`) and its definition cannot be recovered from the reference.  "
+                "Construct the head with second_grad_assumption=True (or set SELFOCC_B200_SECOND_GRAD=1) to opt into the declared "
+                "restatement -- row sums of the Hessian of the trilinear field, see so_field_second_grad in include/selfocc_b200.h "
+                "-- or set return_second_grad=False and drop SecondGradLoss; prepare()/render()/forward_occ() are unaffected")
         from .head_train import forward_train
         return forward_train(self, representation, metas, **kwargs)

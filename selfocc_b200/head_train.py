@@ -94,6 +94,11 @@ def forward_train(head, representation, metas=None, jitter=None, bkgd_rand=None,
                'eik_grad': res['eik_grad'].reshape(total, S, 3), 'uniform_sdf': uniform_sdf, 'inv_s': inv_s}
     if head.return_max_depth:
         outputs['ms_max_depths'] = [max_depth]
+    if head.return_second_grad:
+        # opt-in DECLARED ASSUMPTION (so_field_second_grad): row sums of the Hessian of the trilinear field at the samples
+        t_len = (ts if head.sample_anchor == 'mid' else ts - 0.5 * deltas) * direction_norm[:, None, :]      # ray length at the query point
+        pos = (origin[:, None, :] + direction[:, None, :] * t_len).detach().reshape(-1, 3).contiguous()
+        outputs['second_grad'] = ops.FieldSecondGradFunction.apply(vol_sdf, f.desc, pos).reshape(total, S, 3)
     if head.return_surface_sdf:
         raise NotImplementedError('return_surface_sdf needs the fork\'s `surface_points` definition (unrecoverable, DESIGN.md)')
     if head.return_sample_sdf:

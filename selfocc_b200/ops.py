@@ -346,6 +346,32 @@ class FieldQueryFunction(torch.autograd.Function):
         return gvs, gvf, None, None, None, None
 
 
+class FieldSecondGradFunction(torch.autograd.Function):
+    """`second_grad` at sample points (declared assumption, see so_field_second_grad): (vol_sdf, desc, points[n,3]) -> [n,3],
+    differentiable w.r.t. the volume (it is linear in it)."""
+
+    @staticmethod
+    def forward(ctx, vol_sdf, desc, points):
+        lib = _lib.load()
+        _chk(vol_sdf, name='vol_sdf'); _chk(points, name='points')
+        out = torch.empty(points.shape[0], 3, device=points.device)
+        _lib.check(lib.so_field_second_grad(_p(vol_sdf), C.byref(desc), _p(points), points.shape[0], _p(out), _stream()),
+                   'so_field_second_grad')
+        ctx.desc = desc
+        ctx.save_for_backward(points, vol_sdf)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        points, vol_sdf = ctx.saved_tensors
+        gvs = torch.zeros_like(vol_sdf)
+        _lib.check(lib.so_field_second_grad_backward(C.byref(ctx.desc), _p(points), points.shape[0], _p(g.contiguous()), _p(gvs),
+                                                     _stream()), 'so_field_second_grad_backward')
+        return gvs, None, None
+
+
 class TPVDecodeFunction(torch.autograd.Function):
     """Decode with the fused sm_100a forward.  Backward (training only) recomputes the MLP slab by slab with
     torch/cuBLAS -- bounded memory, never the reference's 750 MB intermediate; a native backward kernel is future work."""
@@ -419,8 +445,10 @@ def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None, out=None)
     return y
 
 
-def linear_supported(K):
-    return K % 96 == 0
+def linear_supported(K, N=None):
+    """Shapes so_linear_3xtf32 accepts (gemm.cu): K = 96 or 192, N a multiple of 4 (16-byte TMA store rows).  Anything
+    else takes cuBLAS in the callers instead of raising SO_ERR_UNSUPPORTED."""
+    return K in (96, 192) and (N is None or N % 4 == 0)
 
 
 def layer_norm(x, gamma, beta, eps=1e-5, add=None):

@@ -185,3 +185,84 @@ def test_head_forward_training_outputs_and_grads():
     for p in planes:
         assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
     assert f.density_net[1].weight.grad.abs().sum() > 0 and f.deviation_network.variance.grad is not None
+
+
+def test_second_grad_matches_double_backward_of_the_oracle_field():
+    """B8 `second_grad` (opt-in declared assumption, so_field_second_grad): row sums of the Hessian of the trilinear field
+    = torch.autograd.grad(grad_sdf.sum(), x) of the oracle's explicit 8-corner field query; backward is exact because the
+    output is linear in the volume."""
+    dev = _dev()
+    from oracle.mapping import GridMeterMappingRef
+    from oracle import render as orender
+    from selfocc_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    margs, aabb = synth.small_mapping(10, 6)
+    m, mref = GridMeterMapping(**margs), GridMeterMappingRef(**margs)
+    sdf = torch.randn(m.size_h, m.size_w, m.size_d, generator=g)
+    lo, hi = torch.tensor(aabb[:3]) - 0.8, torch.tensor(aabb[3:]) + 0.8          # some points outside: zeros padding
+    x = lo + (hi - lo) * torch.rand(4000, 3, generator=g)
+    x64 = x.double().requires_grad_(True)
+    vol64 = sdf[None].double().requires_grad_(True)
+    _, grad_chk = orender.field_query_manual(vol64, mref, x64)
+    _, grad = _manual_grad_of_x(vol64, mref, x64)                  # same gradient, fractions kept differentiable w.r.t. x
+    assert torch.allclose(grad, grad_chk)
+    sg_ref = torch.autograd.grad(grad.sum(), x64, create_graph=True)[0]
+    desc = m.volume_desc(0)
+    vs = synth.pack_sdf_volume(sdf, desc.zpitch).to(dev).requires_grad_(True)
+    sg = ops.FieldSecondGradFunction.apply(vs, desc, x.to(dev).contiguous())
+    assert torch.allclose(sg.detach().cpu().double(), sg_ref.detach(), atol=2e-4, rtol=1e-4)
+    # backward: d (sum c * second_grad) / d volume
+    c = torch.randn(4000, 3, generator=g)
+    (sg * c.to(dev)).sum().backward()
+    gv_ref = torch.autograd.grad((sg_ref * c.double()).sum(), vol64)[0][0]
+    assert torch.allclose(vs.grad[..., :m.size_d].cpu().double(), gv_ref, atol=2e-3, rtol=1e-4)
+
+
+def _manual_grad_of_x(vol, mapping, x):
+    """field_query_manual with the fractions kept differentiable w.r.t. x (meter2grid is piecewise linear in x)."""
+    Cf, H, W, Z = vol.shape
+    g = mapping.meter2grid(x, False)
+    gh, gw, gd = g[:, 0], g[:, 1], g[:, 2]
+    h0, w0, z0 = gh.detach().floor(), gw.detach().floor(), gd.detach().floor()
+    fh, fw, fz = gh - h0, gw - w0, gd - z0
+    h0, w0, z0 = h0.long(), w0.long(), z0.long()
+    dgh = dgw = dgd = 0
+    for dh in (0, 1):
+        for dw in (0, 1):
+            for dz in (0, 1):
+                hh, ww, zz = h0 + dh, w0 + dw, z0 + dz
+                ok = ((hh >= 0) & (hh < H) & (ww >= 0) & (ww < W) & (zz >= 0) & (zz < Z)).to(vol.dtype)
+                v = vol[0, hh.clamp(0, H - 1), ww.clamp(0, W - 1), zz.clamp(0, Z - 1)] * ok
+                wh, w_w, wz = (fh if dh else 1 - fh), (fw if dw else 1 - fw), (fz if dz else 1 - fz)
+                dgh = dgh + (1.0 if dh else -1.0) * w_w * wz * v
+                dgw = dgw + wh * (1.0 if dw else -1.0) * wz * v
+                dgd = dgd + wh * w_w * (1.0 if dz else -1.0) * v
+    xr = x.detach().clone().requires_grad_(True)
+    slopes = torch.autograd.grad(mapping.meter2grid(xr, False).sum(), xr)[0]
+    return None, torch.stack([dgw * slopes[:, 0], dgh * slopes[:, 1], dgd * slopes[:, 2]], -1)
+
+
+def test_head_forward_with_the_shipped_occ_config_options():
+    """config/nuscenes/nuscenes_occ.py:321-322,350: return_second_grad=True, return_sem=True, color_dims=24 -- the training
+    forward refuses without the opt-in and runs (all outputs finite, gradients reach the planes) with it."""
+    dev = _dev()
+    from selfocc_b200.registry import build_head
+    import selfocc_b200.segmentor  # noqa: F401
+    margs, rng = synth.small_mapping(8, 4, rng=20.0, z0=-2.0, z1=4.0)
+    cfg = configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=6, num_layers=1, num_points_cross=(6, 6, 4),
+                                  num_points_self=4, num_samples=64, ray_number=(6, 8), ray_img_size=(90, 160), color_dims=24,
+                                  return_sem=True, ray_sample_mode='cellular')
+    cfg['head'].update(return_second_grad=True, return_uniform_sdf=True)
+    model = build_head(cfg).to(dev).train()
+    l2i, i2l = synth.camera_rig(f=126.6, cx=80., cy=45., height=0.5, radius=0.2)
+    metas = [dict(lidar2img=list(l2i), img2lidar=list(i2l), img_shape=(90, 160))]
+    planes = [p.detach().clone().requires_grad_(True) for p in (model.lifter.tpv_hw, model.lifter.tpv_zh, model.lifter.tpv_wz)]
+    with pytest.raises(NotImplementedError):
+        model.head(representation=planes, metas=metas)
+    model.head.second_grad_assumption = True
+    out = model.head(representation=planes, metas=metas)
+    assert out['second_grad'].shape == (6 * 48, 64, 3) and torch.isfinite(out['second_grad']).all()
+    assert out['sem'][0].shape[-1] == 21
+    loss = out['second_grad'].abs().mean() + out['ms_depths'][0].mean() + out['sem'][0].sum() * 1e-3
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in planes)

@@ -1,7 +1,11 @@
 """CPU: registry / constructor / state_dict contract of the drop-in modules (no kernel calls)."""
+import os
+import sys
 import torch
 import pytest
 from selfocc_b200 import synth, configs
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from selfocc_b200.registry import MODELS, build_head
 import selfocc_b200.segmentor  # noqa: F401  (registers everything)
 
@@ -136,3 +140,84 @@ def test_layer_token_buffer_detection():
     assert _whole((views[1], views[0], views[2]), split) is None                 # other order
     wide = torch.randn(1, 11, 8)
     assert _whole(torch.split(wide[..., :4], split, 1), split) is None           # column slice of a wider buffer
+
+
+def test_modules_register_into_a_real_mmengine_style_registry(tmp_path):
+    """Boundary: with mmengine importable the classes must land in mmengine's MODELS registry (the one
+    mmseg.models.builder.build_head reads, base_segmentor.py:27-32) and build from the reference's config dicts through it.
+    mmengine is not installed here, so a minimal stand-in with the same public surface (Registry.register_module as plain /
+    called decorator, .get, .build(cfg) -> cls(**cfg without 'type')) is put on the path in a subprocess."""
+    import subprocess
+    import textwrap
+    pkg = tmp_path / 'mmengine'
+    pkg.mkdir()
+    (pkg / '__init__.py').write_text('')
+    (pkg / 'registry.py').write_text(textwrap.dedent('''
+        class Registry:
+            def __init__(self, name):
+                self.name, self.module_dict = name, {}
+            def register_module(self, name=None, force=False, module=None):
+                def _reg(cls):
+                    key = name or cls.__name__
+                    if key in self.module_dict and not force:
+                        raise KeyError(key + ' is already registered in ' + self.name)
+                    self.module_dict[key] = cls
+                    return cls
+                return _reg(module) if module is not None else _reg
+            def get(self, key):
+                return self.module_dict.get(key)
+            def build(self, cfg, *args, **kwargs):
+                cfg = dict(cfg)
+                cls = self.get(cfg.pop('type'))
+                if cls is None:
+                    raise KeyError('not in the ' + self.name + ' registry')
+                return cls(**cfg)
+        MODELS = Registry('model')
+    '''))
+    code = textwrap.dedent('''
+        import json, os, sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import mmengine.registry as mr
+        import selfocc_b200.segmentor
+        from selfocc_b200 import registry
+        assert registry.HAVE_MMENGINE and registry.MODELS is mr.MODELS
+        names = ['TPVQueryLifter', 'TPVFormerEncoder', 'TPVFormerLayer', 'TPVPositionalEncoding', 'CrossViewHybridAttention',
+                 'TPVCrossAttention', 'BEVCrossAttention', 'BEVDeformableAttention', 'NeuSHead']
+        missing = [n for n in names if mr.MODELS.get(n) is None]
+        assert not missing, missing
+        cfgs = json.load(open(os.path.join(%r, 'tests', 'golden', 'reference_model_cfgs.json')))
+        m = cfgs['nuscenes/nuscenes_depth.py']
+        lifter, encoder, head = (mr.MODELS.build(m[k]) for k in ('lifter', 'encoder', 'head'))     # what build_head does
+        assert type(head).__name__ == 'NeuSHead' and len(encoder.layers) == 4
+        print('OK', len(mr.MODELS.module_dict))
+    ''') % (str(tmp_path), ROOT_DIR, ROOT_DIR)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout + r.stderr
+
+
+def test_head_checkpoint_key_map():
+    """INTEGRATION.md section 1: field parameters stored under another module path (a fork checkpoint) load into
+    head.model.field.* -- by unambiguous suffix, or through an explicit {regex: replacement} map."""
+    model = build_head(_small_cfg())
+    sd = model.state_dict()
+    moved = {}
+    for k, v in sd.items():
+        if k.startswith('head.model.field.density_net.') or k.startswith('head.model.field.deviation_network.'):
+            moved[k.replace('head.model.field.', 'head.model.some_fork_field.')] = v + 1.0
+        else:
+            moved[k] = v
+    m2 = build_head(_small_cfg())
+    missing, unexpected = m2.load_state_dict(dict(moved), strict=False)
+    assert not missing and not unexpected
+    for k, v in m2.head.state_dict().items():
+        if 'density_net' in k or 'deviation_network' in k:
+            assert torch.equal(v, sd['head.' + k] + 1.0)
+    # explicit map
+    m3 = build_head(_small_cfg())
+    m3.head.checkpoint_key_map = {r'^net\.mlp\.': 'model.field.density_net.', r'^net\.var$': 'model.field.deviation_network.variance'}
+    alt = {}
+    for k, v in sd.items():
+        k2 = k.replace('head.model.field.density_net.', 'head.net.mlp.').replace('head.model.field.deviation_network.variance', 'head.net.var')
+        alt[k2] = v
+    missing, unexpected = m3.load_state_dict(alt, strict=False)
+    assert not missing and not unexpected

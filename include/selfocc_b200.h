@@ -205,6 +205,18 @@ int so_field_second_grad(const float* vol_sdf, const so_volume_desc* vol_host, c
 int so_field_second_grad_backward(const so_volume_desc* vol_host, const float* points, int64_t n, const float* g_second_grad,
                                   float* g_vol_sdf, void* stream);
 
+/* 8f-3  device-side DepthMetric step (utils/metric_util.py:247-279,311-349; eval_novel_depth.py:174-200).
+ * so_depth_metric_sample: depth_pred [N,h,w], loc [N,n,2] in [0,1] (x,y) -> sampled [N,n] with the arithmetic of
+ *   F.grid_sample(pred, loc*2-1, bilinear, padding_mode='border', align_corners=True).
+ * so_depth_metric_sums: per camera, over points with mask != 0 and pred' = clamp(scale[cam] * sampled, 1e-3, 80)
+ *   (scale NULL = 1): sums [N,8] = (sum |gt-pred'|/gt, sum (gt-pred')^2/gt, sum (gt-pred')^2, sum (log gt - log pred')^2,
+ *   #(thresh < 1.25), #(< 1.25^2), #(< 1.25^3), #points); the metrics are sums / #points (rmse: sqrt).  One CTA per
+ *   camera, deterministic. */
+int so_depth_metric_sample(const float* depth_pred, const float* loc, int32_t N, int32_t n, int32_t h, int32_t w,
+                           float* sampled, void* stream);
+int so_depth_metric_sums(const float* sampled, const float* depth_gt, const uint8_t* mask, const float* scale, int32_t N,
+                         int32_t n, float* sums, void* stream);
+
 /* B12  field query at arbitrary points.  Replaces field.forward_sdfnetwork / forward_geonetwork
  * as used by NeuSHead.get_uniform_sdf (neus_head.py:265-293).  points [n,3] metres ->
  * sdf [n], grad [n,3] (NULL ok), feat [n, n_feat] raw decoded channels 1.. (NULL ok). */

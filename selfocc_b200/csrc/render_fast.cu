@@ -28,10 +28,13 @@
 #define SO_RF_MIN_CTAS_RGB 4
 #endif
 #ifndef SO_RF_UNROLL
-#define SO_RF_UNROLL 1
+#define SO_RF_UNROLL 2
 #endif
 #ifndef SO_RF_EXIT_T
 #define SO_RF_EXIT_T 1e-9f
+#endif
+#ifndef SO_RF_EXIT_EVERY
+#define SO_RF_EXIT_EVERY 2      // the exit vote is taken every 2nd sample (power of two)
 #endif
 
 namespace so {
@@ -78,7 +81,7 @@ __device__ __forceinline__ void composite(RayAcc& a, float alpha, float mid, flo
   float wn = w * rsqrtf(fmaxf(fmaf(gx, gx, fmaf(gy, gy, gz * gz)), 1e-24f));   // F.normalize(eps=1e-12)
   a.n0 = fmaf(wn, gx, a.n0); a.n1 = fmaf(wn, gy, a.n1); a.n2 = fmaf(wn, gz, a.n2);
   // max-depth candidate (neus_head.py:430-438): delta is a positive per-ray constant here, so argmax(w / delta) = argmax(w)
-  if (w > a.best) { a.best = w; a.best_i = s; a.best_mid = mid; }
+  if (w > a.best) { a.best = w; a.best_i = s; }     // best_mid is recomputed from best_i after the loop (same fp32 formula)
   w_out = w;
 }
 
@@ -240,12 +243,13 @@ render_packed_kernel(VolumeDev V, const void* __restrict__ pack, RayDev R, Rende
         const float r0 = fmaxf(c2.x, 0.f), r1 = fmaxf(c2.y, 0.f), r2 = fmaxf(fmaf(bl, kC0, 0.5f), 0.f);
         a.c_r = fmaf(w, r0, a.c_r); a.c_g = fmaf(w, r1, a.c_g); a.c_b = fmaf(w, r2, a.c_b);
       }
-      if (!DBG && __all_sync(kFull, a.T < SO_RF_EXIT_T)) break;
+      if (!DBG && (s & (SO_RF_EXIT_EVERY - 1)) == SO_RF_EXIT_EVERY - 1 && __all_sync(kFull, a.T < SO_RF_EXIT_T)) break;
     }
   }
   if (!valid) return;
   const float eps_len = 1.1920928955078125e-07f * nrm;   // torch.finfo(float32).eps * |dir| (neus_head.py:431)
-  if (delta_c < eps_len) { a.best_i = 0; a.best_mid = m_first; }   // every candidate is 0: first index
+  if (delta_c < eps_len) a.best_i = 0;                   // every candidate is 0: first index
+  a.best_mid = fmaf(((float)a.best_i + 0.5f) * G.step, G.span, tn);   // (i + 1/2) / S is exact: the loop's mid_i bit for bit
 
   const long long chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
   const float lo = __ldg(ws + 2 * chunk), hi = __ldg(ws + 2 * chunk + 1);

@@ -97,12 +97,16 @@ class Img2LiDAR(nn.Module):
         if not isinstance(kws, list):
             kws = [kws]
         M = torch.cat([_metas_matrix(metas, k, device) for k in kws], 1).clone()   # B, N, 4, 4
-        if self.novel_view is not None:
-            a = math.radians(self.novel_view[3])
-            R = torch.tensor([[math.cos(a), -math.sin(a), 0.], [math.sin(a), math.cos(a), 0.], [0., 0., 1.]], device=device)
-            M[..., :3, :3] = R[None, None] @ M[..., :3, :3]
-            for i in range(3):
-                M[..., i, 3] = M[..., i, 3] + self.novel_view[i]
+        return self.apply_novel_view(M) if self.novel_view is not None else M
+
+    def apply_novel_view(self, M):
+        """img2lidar.py:51-61: z-rotation (degrees) of the 3x3 block, then an xyz translation of the origin.  M [B, N, 4, 4]."""
+        a = math.radians(self.novel_view[3])
+        R = torch.tensor([[math.cos(a), -math.sin(a), 0.], [math.sin(a), math.cos(a), 0.], [0., 0., 1.]], device=M.device)
+        M = M.clone()
+        M[..., :3, :3] = R[None, None] @ M[..., :3, :3]
+        for i in range(3):
+            M[..., i, 3] = M[..., i, 3] + self.novel_view[i]
         return M
 
     def forward(self, metas, rays):
@@ -324,6 +328,70 @@ class NeuSHead(nn.Module):
         if self.return_sem:
             outputs['sem'] = [shp(out['sem'], out['sem'].shape[-1])]
         return outputs
+
+    @torch.no_grad()
+    def render_poses(self, metas=None, poses=None, batch=0, want=None, **kwargs):
+        """8f-3: K renders of the prepared frame in ONE launch.  The reference's novel-depth evaluation issues one
+        ``head.render`` per source pose after a single ``prepare`` (eval_novel_depth.py:159-172,
+        ``metas['render_img2lidar'] = temImg2lidars[source_id]``); here ``poses`` = those K matrix sets ([K, N, 4, 4] array /
+        tensor or a list of K [N, 4, 4]; default: ``metas[0]['temImg2lidars']``) are rendered as K * N cameras of one ray
+        set.  Every pose keeps its own expected-depth clip (the renderer clips per ``self.model(ray_bundle)`` call), so the
+        result equals K separate ``render`` calls; returns the ``render`` dict with a leading pose axis: ms_depths[0] is
+        [K, N, R].  ``batch > 0`` (the reference's chunking) falls back to K launches when a chunk would straddle poses."""
+        f = self.model.field
+        if f.vol_sdf is None:
+            raise RuntimeError('render_poses() called before prepare()/forward(): no decoded volume')
+        dev = f.vol_sdf.device
+        if poses is None:
+            poses = metas[0]['temImg2lidars']
+        P = torch.as_tensor(np.asarray([np.asarray(p) for p in poses]) if not torch.is_tensor(poses) else poses,
+                            dtype=torch.float32, device=dev)
+        assert P.dim() == 4 and P.shape[-2:] == (4, 4), 'poses must be [K, N, 4, 4]'
+        K, N = P.shape[:2]
+        sampler = self._sampler()
+        grid = sampler.draw()
+        rays = sampler.table(grid)
+        R = rays.shape[0]
+        per_pose = N * R
+        chunk_len = per_pose
+        if batch > 0:
+            chunks = int(math.ceil(per_pose * 1.0 / batch))
+            chunk_len = int(math.ceil(per_pose / chunks))
+            if per_pose % chunk_len:              # a chunk would straddle two poses: keep the reference's exact clip groups
+                outs = []
+                for k in range(K):
+                    m2 = [dict(metas[0], render_img2lidar=P[k])]
+                    saved = self.img2lidar.trans_kw, self.img2lidar.trans_kw_eval
+                    self.img2lidar.trans_kw = self.img2lidar.trans_kw_eval = ['render_img2lidar']
+                    try:
+                        outs.append(self.render(metas=m2, batch=batch))
+                    finally:
+                        self.img2lidar.trans_kw, self.img2lidar.trans_kw_eval = saved
+                keys = [k for k in outs[0] if isinstance(outs[0][k], list)]
+                merged = {k: [torch.cat([o[k][0] for o in outs], 0)] for k in keys}
+                merged['ms_rays'] = rays
+                return merged
+        M = P.reshape(K * N, 4, 4).clone()
+        if self.img2lidar.novel_view is not None:
+            M = self.img2lidar.apply_novel_view(M[None])[0]
+        has_rgb = f.color_dims >= 3
+        if want is None:
+            want = ['depth', 'acc', 'normal_vis'] + (['max_depth'] if self.return_max_depth else []) + (['rgb'] if has_rgb else [])
+        rd = ops.make_ray_desc(K * N, grid=grid, n_pix=R, chunk_len=chunk_len)
+        bk = torch.rand(K * per_pose, 3, device=dev) if (self.render_bkgd == 'random' and 'rgb' in want) else None
+        out = ops.render_infer(f.vol_sdf, f.vol_feat, f.desc, M.contiguous(), rd, self._params(False),
+                               pix=None if grid is not None else rays.contiguous(), bkgd_rand=bk, want=want, pack=f.render_pack())
+        shp = lambda t, *tail: t.reshape(K, N, R, *tail)
+        res = {'ms_rays': rays}
+        names = dict(depth='ms_depths', acc='ms_accs', max_depth='ms_max_depths')
+        for k, v in out.items():
+            if k in names:
+                res[names[k]] = [shp(v)]
+            elif k == 'rgb':
+                res['ms_colors'] = [shp(v, 3)]
+            elif k == 'normal_vis':
+                res['vis_normal'] = [shp(v, 3)]
+        return res
 
     def get_uniform_sdf(self, aabb, resolution, device, shift=False):
         """neus_head.py:265-293."""

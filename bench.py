@@ -51,6 +51,8 @@ def parse():
     ap.add_argument('--color-dims', type=int, default=3, choices=[0, 3],
                     help='3: the configs[2] head (nuscenes_novel_depth.py:326); 0: depth-only head (nuscenes_depth.py)')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling (one frame sharded over the ranks) measurement')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='which measurement is the headline `value`')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-style eager-PyTorch-on-GPU side figure')
     return ap.parse_args()
 
@@ -174,13 +176,26 @@ def run_b200(args):
         model.head.prepare(representation=r['representation'], metas=m)
         return model.head.render(metas=m, batch=0)
 
+    pending = []                                       # (work, buffers): the previous frame's gather, still in flight
+
+    def gather_join():
+        while pending:
+            pending.pop()[0].wait()
+
     def gather(out):
+        """The one collective of the weak mode (depth / max-depth / RGB of every rank's frame), issued ASYNCHRONOUSLY: NCCL runs
+        it on its own stream while the compute stream already lifts the next frame; it is joined one step later (and by
+        `gather_join` at the end of the timed region, so every gather is paid for inside the region)."""
         if world == 1:
             return out['ms_depths'][0]
         cols = [out['ms_depths'][0].reshape(-1, 1), out['ms_max_depths'][0].reshape(-1, 1)]
         if has_rgb:
             cols.append(out['ms_colors'][0].reshape(-1, 3))
-        return all_gather_rays(torch.cat(cols, -1), world * rays_per_frame)   # the one collective: depth / max-depth / RGB
+        local = torch.cat(cols, -1)
+        full = local.new_empty((world * rays_per_frame, local.shape[1]))
+        gather_join()                                                  # frame k-1's gather must be done before frame k's starts
+        pending.append((dist.all_gather_into_tensor(full, local, async_op=True), (full, local)))
+        return full
 
     def timed(fn, K, W, sampler=None, sample_clocks=False, finalize=None):
         if sampler:
@@ -225,10 +240,29 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     _lib.profile_enable(True)
     sampler = ClockSampler(local) if rank == 0 else None
-    total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler, sample_clocks=True)
+    total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler, sample_clocks=True,
+                                       finalize=gather_join if world > 1 else None)
     prof = _lib.profile_read()
     ms_per_step = total_ms / K
     value = world * rays_per_frame / (ms_per_step * 1e-3)
+
+    # ---- strong scaling of ONE frame: query-sharded lifting (one all_gather of the planes per layer), slab-sharded
+    # decode, ray-sharded render, one final all_gather -- selfocc_b200/dist.py.  Total work is fixed as N grows.
+    strong = None
+    if not args.no_strong:
+        from selfocc_b200.dist import ShardedLifter, frame_sharded
+        _lib.profile_enable(False)
+        sl = ShardedLifter(model.encoder)
+        feats_0 = feats_d
+        if world > 1:                                                  # every rank works on rank 0's frame
+            feats_0 = [f.clone() for f in feats_d]
+            for f in feats_0:
+                dist.broadcast(f, 0)
+        s_ms, _, _ = timed(lambda: frame_sharded(model, feats_0, metas_d, lifter=sl), K, W)
+        strong = {'value': rays_per_frame / (s_ms / K * 1e-3), 'unit': 'rays/s', 'ms_per_step': s_ms / K, 'scaling': 'strong',
+                  'frames_per_step': 1, 'parallelism': 'query-sharded lifting (1 all_gather/layer) + slab-sharded decode + '
+                  'ray-sharded render + 1 all_gather over %d rank(s)' % world}
+        _lib.profile_enable(True)
 
     # ---- e2e: same step through the public module API with HOST inputs / outputs inside the timed region
     e2e = None
@@ -250,7 +284,7 @@ def run_b200(args):
         _lib.profile_enable(False)
         # the same frames through selfocc_b200.pipeline.FramePipeline: upload of frame k+1 and download of frame k overlap
         # the compute of their neighbours (every step still uploads its inputs and downloads its result inside the region)
-        step_fn, finalize, mode = step_e2e, None, 'serial copies on the compute stream'
+        step_fn, finalize, mode = step_e2e, (gather_join if world > 1 else None), 'serial copies on the compute stream'
         if not args.no_e2e_pipeline:
             try:
                 from selfocc_b200.pipeline import FramePipeline
@@ -270,7 +304,7 @@ def run_b200(args):
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 ok = int(flag.item())
             if ok:
-                step_fn, finalize, mode = step_pipe, pipe.drain, 'FramePipeline: H2D of frame k+1 / D2H of frame k overlap compute'
+                step_fn, finalize, mode = step_pipe, (lambda: (pipe.drain(), gather_join())), 'FramePipeline: H2D of frame k+1 / D2H of frame k overlap compute'
             else:
                 mode += why
         e_ms, _, _ = timed(step_fn, K, W, finalize=finalize)
@@ -313,10 +347,16 @@ def run_b200(args):
                        'tpv': '257x257x31x96', 'fpn_levels': shapes, 'encoder_layers': 4,
                        'color_dims': args.color_dims, 'render_bkgd': 'random' if has_rgb else 'white',
                        'outputs': 'depth, max_depth, acc, normal' + (', rgb' if has_rgb else ''),
-                       'frames_per_step': world, 'parallelism': 'dp%d frames + 1 all_gather' % world,
+                       'frames_per_step': world, 'parallelism': 'dp%d frames + 1 all_gather (async, overlaps the next lift)' % world,
                        'l2_flush_between_steps': True},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'kernel_ms_per_step': breakdown}
+    if strong is not None:
+        line['strong_scaling'] = strong
+        if args.scaling == 'strong':                                   # make the one-frame-sharded number the headline
+            line['weak_scaling'] = {'value': value, 'ms_per_step': ms_per_step, 'scaling': 'weak'}
+            line.update(value=strong['value'], ms_per_step=strong['ms_per_step'], scaling='strong')
+            line['config'].update(frames_per_step=1, parallelism=strong['parallelism'])
     if world == 1 and not args.no_train_probe:
         try:
             line['roofline_train_form'] = train_form_probe(dev, hbm_peak)

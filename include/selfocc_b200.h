@@ -84,6 +84,11 @@ typedef struct so_volume_desc {
 int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C,
                   const float* w1, const float* b1, const float* w2, const float* b2,
                   const so_volume_desc* vol_host, float* vol_sdf, float* vol_feat, void* stream);
+/* Same, for the row range [h_begin, h_begin + h_count) of the volume only (voxel-sharded decode: every rank decodes its
+ * slab of h rows into the full-size buffers and one all_gather assembles the volume).  Other rows untouched. */
+int so_tpv_decode_rows(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C, const float* w1,
+                       const float* b1, const float* w2, const float* b2, const so_volume_desc* vol_host, int32_t h_begin,
+                       int32_t h_count, float* vol_sdf, float* vol_feat, void* stream);
 
 /* Test hook: force the fp32 SIMT decode kernel (default: the tcgen05 3xTF32 kernel whenever C % 32 == 0). */
 int so_tpv_decode_force_simt(int on);

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kThreads) tpv_decode_kernel(
     const float* __restrict__ hw, const float* __restrict__ zh, const float* __restrict__ wz,
     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
     const float* __restrict__ b2, int H, int W, int Z, int zpitch, int n_out, int feat_pitch,
-    float* __restrict__ vol_sdf, float* __restrict__ vol_feat) {
+    float* __restrict__ vol_sdf, float* __restrict__ vol_feat, int h_begin) {
   constexpr int LD = C + 4;
   constexpr int TN = C / 16;  // output columns per thread (strided by 16)
   extern __shared__ __align__(16) float smem[];
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kThreads) tpv_decode_kernel(
   float* b2s = b1s + C;             // [kMaxOut]
 
   const int tid = threadIdx.x;
-  const int h = blockIdx.y;
+  const int h = h_begin + blockIdx.y;     // row range [h_begin, h_begin + gridDim.y): so_tpv_decode_rows
   const int v0 = blockIdx.x * kRows;
   const int WZ = W * Z;
 
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kDecThreads, 1)
 tpv_decode_tc_kernel(const float* __restrict__ hw, const float* __restrict__ zh, const float* __restrict__ wz,
                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                      const float* __restrict__ b2, int C, int H, int W, int Z, int zpitch, int n_out, int feat_pitch,
-                     float* __restrict__ vol_sdf, float* __restrict__ vol_feat, int tiles_per_row, int n_tiles) {
+                     float* __restrict__ vol_sdf, float* __restrict__ vol_feat, int tiles_per_row, int n_tiles, int h_begin) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const DecSmem L = dec_smem(C, n_out);
@@ -210,7 +210,7 @@ tpv_decode_tc_kernel(const float* __restrict__ hw, const float* __restrict__ zh,
     const float inv_z = 1.0f / (float)Z;
     int s = 0; uint32_t ph = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int h = t / tiles_per_row, v0 = (t - h * tiles_per_row) * kBM;
+      const int hr = t / tiles_per_row, h = h_begin + hr, v0 = (t - hr * tiles_per_row) * kBM;
       // (w, z) of this thread's four voxel rows; (v + 1/2) / Z is at least 1/(2Z) away from an integer, so the float
       // floor is exact
       int vv[4], ww[4], zz[4];
@@ -292,7 +292,7 @@ tpv_decode_tc_kernel(const float* __restrict__ hw, const float* __restrict__ zh,
     const int r = q * 32 + lane;
     int acc = 0; uint32_t acc_ph = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int h = t / tiles_per_row, v = (t - h * tiles_per_row) * kBM + r;
+      const int hr = t / tiles_per_row, h = h_begin + hr, v = (t - hr * tiles_per_row) * kBM + r;
       mbar_wait(tmem_full + acc, acc_ph);
       tc_fence_after();
       float out[NOUT];
@@ -337,7 +337,7 @@ __global__ void zero_pad_kernel(float* vol_sdf, long long columns, int Z, int zp
 
 template <int C>
 int launch_decode(const float* hw, const float* zh, const float* wz, const float* w1, const float* b1, const float* w2,
-                  const float* b2, const so_volume_desc* d, float* vol_sdf, float* vol_feat, cudaStream_t st) {
+                  const float* b2, const so_volume_desc* d, float* vol_sdf, float* vol_feat, int h_begin, int h_count, cudaStream_t st) {
   constexpr int LD = C + 4;
   size_t smem = sizeof(float) * ((size_t)kRows * LD + (size_t)C * LD + (size_t)kMaxOut * C + C + kMaxOut);
   static PerDeviceOnce attr_simt;
@@ -345,10 +345,10 @@ int launch_decode(const float* hw, const float* zh, const float* wz, const float
     return check_cuda(cudaFuncSetAttribute(tpv_decode_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
   if (rc_attr) return rc_attr;
-  dim3 grid((unsigned)ceil_div64((int64_t)d->W * d->Z, kRows), (unsigned)d->H);
+  dim3 grid((unsigned)ceil_div64((int64_t)d->W * d->Z, kRows), (unsigned)h_count);
   ProfScope prof(1, st);
   tpv_decode_kernel<C><<<grid, kThreads, smem, st>>>(hw, zh, wz, w1, b1, w2, b2, d->H, d->W, d->Z, d->zpitch,
-                                                       1 + d->n_feat, d->feat_pitch, vol_sdf, vol_feat);
+                                                       1 + d->n_feat, d->feat_pitch, vol_sdf, vol_feat, h_begin);
   note_launch(1);
   return check_launch();
 }
@@ -364,16 +364,27 @@ extern "C" int so_tpv_decode_force_simt(int on) { g_decode_force_simt = on != 0;
 extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C, const float* w1,
                              const float* b1, const float* w2, const float* b2, const so_volume_desc* d,
                              float* vol_sdf, float* vol_feat, void* stream) {
+  if (!d) return SO_ERR_INVALID_ARG;
+  return so_tpv_decode_rows(tpv_hw, tpv_zh, tpv_wz, C, w1, b1, w2, b2, d, 0, d->H, vol_sdf, vol_feat, stream);
+}
+
+// Row range [h_begin, h_begin + h_count) of the volume only (voxel-sharded decode across GPUs: every rank decodes its
+// slab of h rows into the full-size volume buffer, one all_gather assembles it).  Rows outside the range are untouched.
+extern "C" int so_tpv_decode_rows(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C, const float* w1,
+                                  const float* b1, const float* w2, const float* b2, const so_volume_desc* d, int32_t h_begin,
+                                  int32_t h_count, float* vol_sdf, float* vol_feat, void* stream) {
   if (!tpv_hw || !tpv_zh || !tpv_wz || !w1 || !b1 || !w2 || !b2 || !vol_sdf) return SO_ERR_INVALID_ARG;
   int rc = validate_volume(d);
   if (rc) return rc;
+  if (h_begin < 0 || h_count < 0 || h_begin + h_count > d->H) return SO_ERR_INVALID_ARG;
+  if (h_count == 0) return SO_OK;
   if (d->n_feat > 0 && !vol_feat) return SO_ERR_INVALID_ARG;
   if (1 + d->n_feat > kMaxOut) return SO_ERR_UNSUPPORTED;
   if (d->H > 65535) return SO_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (d->zpitch > d->Z) {
-    long long n = (long long)d->H * d->W * (d->zpitch - d->Z);
-    zero_pad_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(vol_sdf, (long long)d->H * d->W, d->Z, d->zpitch);
+    long long cols = (long long)h_count * d->W, n = cols * (d->zpitch - d->Z);
+    zero_pad_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(vol_sdf + (long long)h_begin * d->W * d->zpitch, cols, d->Z, d->zpitch);
     note_launch(1);
   }
   if (C % 32 == 0 && C >= 32 && C <= 128 && !g_decode_force_simt) {
@@ -389,11 +400,11 @@ extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const flo
            })))
         return rc;
       const int tiles_per_row = (int)ceil_div64((int64_t)d->W * d->Z, kBM);
-      const int n_tiles = tiles_per_row * d->H;
+      const int n_tiles = tiles_per_row * h_count;
       const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
       ProfScope prof(1, st);
 #define SO_DEC_TC(NO) tpv_decode_tc_kernel<NO><<<grid, kDecThreads, Ls.total, st>>>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, C, d->H, d->W, d->Z, \
-                                                                                  d->zpitch, n_out, d->feat_pitch, vol_sdf, vol_feat, tiles_per_row, n_tiles)
+                                                                                  d->zpitch, n_out, d->feat_pitch, vol_sdf, vol_feat, tiles_per_row, n_tiles, h_begin)
       if (n_out == 1) SO_DEC_TC(1); else if (n_out <= 4) SO_DEC_TC(4); else SO_DEC_TC(32);
 #undef SO_DEC_TC
       note_launch(1);
@@ -401,10 +412,10 @@ extern "C" int so_tpv_decode(const float* tpv_hw, const float* tpv_zh, const flo
     }
   }
   switch (C) {
-    case 32: return launch_decode<32>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, st);
-    case 64: return launch_decode<64>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, st);
-    case 96: return launch_decode<96>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, st);
-    case 128: return launch_decode<128>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, st);
+    case 32: return launch_decode<32>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, h_begin, h_count, st);
+    case 64: return launch_decode<64>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, h_begin, h_count, st);
+    case 96: return launch_decode<96>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, h_begin, h_count, st);
+    case 128: return launch_decode<128>(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, d, vol_sdf, vol_feat, h_begin, h_count, st);
     default: return SO_ERR_UNSUPPORTED;
   }
 }

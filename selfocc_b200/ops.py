@@ -30,8 +30,10 @@ def _stream():
 
 
 # --------------------------------------------------------------------------------------- B5
-def tpv_decode(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, desc):
-    """planes [H*W,C], [Z*H,C], [W*Z,C] + MLP -> (vol_sdf [H,W,zpitch], vol_feat [H,W,Z,feat_pitch] | None)."""
+def tpv_decode(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, desc, rows=None, out=None):
+    """planes [H*W,C], [Z*H,C], [W*Z,C] + MLP -> (vol_sdf [H,W,zpitch], vol_feat [H,W,Z,feat_pitch] | None).
+    rows=(h_begin, h_count): decode that slab of h rows only (voxel-sharded decode); out=(vol_sdf, vol_feat): write into
+    existing full-size buffers (rows outside the slab are left untouched)."""
     lib = _lib.load()
     for n, t in (('tpv_hw', tpv_hw), ('tpv_zh', tpv_zh), ('tpv_wz', tpv_wz), ('w1', w1), ('b1', b1), ('w2', w2), ('b2', b2)):
         _chk(t, name=n)
@@ -40,12 +42,18 @@ def tpv_decode(tpv_hw, tpv_zh, tpv_wz, w1, b1, w2, b2, desc):
         and tpv_wz.numel() == desc.W * desc.Z * Cc, 'plane shapes do not match the mapping'
     assert w1.shape == (Cc, Cc) and w2.shape == (1 + desc.n_feat, Cc)
     dev = tpv_hw.device
-    vol_sdf = torch.empty(desc.H, desc.W, desc.zpitch, device=dev, dtype=torch.float32)
-    vol_feat = torch.empty(desc.H, desc.W, desc.Z, desc.feat_pitch, device=dev, dtype=torch.float32) if desc.n_feat else None
+    if out is not None:
+        vol_sdf, vol_feat = out
+        _chk(vol_sdf, name='vol_sdf'); _chk(vol_feat, name='vol_feat')
+        assert vol_sdf.shape == (desc.H, desc.W, desc.zpitch)
+    else:
+        vol_sdf = torch.empty(desc.H, desc.W, desc.zpitch, device=dev, dtype=torch.float32)
+        vol_feat = torch.empty(desc.H, desc.W, desc.Z, desc.feat_pitch, device=dev, dtype=torch.float32) if desc.n_feat else None
+    h0, hc = (0, desc.H) if rows is None else rows
     if vol_feat is not None and desc.feat_pitch > desc.n_feat:
-        vol_feat.zero_()
-    _lib.check(lib.so_tpv_decode(_p(tpv_hw), _p(tpv_zh), _p(tpv_wz), Cc, _p(w1), _p(b1), _p(w2), _p(b2), C.byref(desc),
-                                 _p(vol_sdf), _p(vol_feat), _stream()), 'so_tpv_decode')
+        vol_feat[h0:h0 + hc].zero_()
+    _lib.check(lib.so_tpv_decode_rows(_p(tpv_hw), _p(tpv_zh), _p(tpv_wz), Cc, _p(w1), _p(b1), _p(w2), _p(b2), C.byref(desc),
+                                      int(h0), int(hc), _p(vol_sdf), _p(vol_feat), _stream()), 'so_tpv_decode_rows')
     return vol_sdf, vol_feat
 
 

@@ -184,6 +184,9 @@ int so_render_train_forward(const float* vol_sdf, const float* vol_feat, const s
 /* Test hook: force the one-ray-per-warp forward kernel (default: the batched-ray kernel whenever the mapping is affine,
  * num_samples is a power of two >= 64, the cos-anneal is finished and no semantics are rendered). */
 int so_render_train_force_fwd32(int on);
+/* Test hook: render 24-channel feature volumes through the generic (any channel count) semantic path instead of the
+ * vectorised 3 rgb + 21 class specialisation (config/nuscenes/nuscenes_occ.py:350). */
+int so_render_train_force_sem_generic(int on);
 
 /* Backward of so_render_train_forward w.r.t. the decoded volume and inv_s.  Incoming gradients (NULL = zero):
  * g_depth, g_acc [n], g_rgb [n,3], g_sem [n,n_feat-3], g_weights, g_sdf [n,S], g_eik [n,S,3].  Results are

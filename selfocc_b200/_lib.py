@@ -51,6 +51,7 @@ SIGNATURES = {
     'so_tpv_decode_rows': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _I, _I, _P, _P, _P]),
     'so_tpv_decode_force_simt': (C.c_int, [C.c_int]),
     'so_render_train_force_fwd32': (C.c_int, [C.c_int]),
+    'so_render_train_force_sem_generic': (C.c_int, [C.c_int]),
     'so_render_workspace_floats': (C.c_int64, [_L]),
     'so_render_infer': (C.c_int, [_P, _P, C.POINTER(VolumeDesc), _P, _P, C.POINTER(RayDesc), C.POINTER(RenderParams),
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

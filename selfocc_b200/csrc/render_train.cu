@@ -11,6 +11,13 @@
 #define SO_TRAIN_FWD_MIN_CTAS 8   // 64 registers: 0.122 ms vs 0.153 ms at 4 CTAs/SM (cfg-5 sizes); the kernel is latency-bound
 #endif
 
+#ifndef SO_TRAIN_FWD24_MIN_CTAS
+#define SO_TRAIN_FWD24_MIN_CTAS 3    // 24-channel semantic forward: 168 registers, no spills
+#endif
+#ifndef SO_TRAIN_BWD24_MIN_CTAS
+#define SO_TRAIN_BWD24_MIN_CTAS 3    // 24-channel semantic backward: 168 registers + 328 B of L1-resident spills (2: 255 registers, 44 B)
+#endif
+
 namespace so {
 
 constexpr int kTrainMaxChunks = 8;  // S <= 256
@@ -122,11 +129,61 @@ __device__ __forceinline__ void sample_colour(const VolumeDev& V, const RenderDe
   }
 }
 
+// ---- the shipped semantic configuration (config/nuscenes/nuscenes_occ.py:350: color_dims = 24 = 3 rgb + 21 classes) --------
+// SEM template parameter of the one-ray-per-warp kernels: 0 = no semantics, 1 = any channel count (runtime loops over
+// scalar gathers), 24 = exactly 24 feature channels with feat_pitch 24: a voxel's 96 bytes are read / accumulated as six
+// float4 (48 LDG.128 instead of 192 LDG.32 per sample; 48 128-bit reductions instead of 192 atomics in the backward) and every
+// per-class array has a compile-time size, so nothing lives in local memory (the runtime-count arrays of SEM = 1 spill:
+// 115-152 LDL/STL per sample, profiles/r1_sass_loop_mix.txt).
+constexpr int kSem24 = 21;
+
+__device__ __forceinline__ void gather_feat24(const VolumeDev& v, const Taps& t, float out[24]) {
+#pragma unroll
+  for (int i = 0; i < 24; ++i) out[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int dh = k >> 2, dw = (k >> 1) & 1, dz = k & 1;
+    float wgt = (dh ? t.fh * t.mh1 : (1.f - t.fh) * t.mh0) * (dw ? t.fw * t.mw1 : (1.f - t.fw) * t.mw0) *
+                (dz ? t.fz * t.mz1 : (1.f - t.fz) * t.mz0);
+    int h = min(max(t.h0 + dh, 0), v.H - 1), w = min(max(t.w0 + dw, 0), v.W - 1), z = min(max(t.z0 + dz, 0), v.Z - 1);
+    const float4* p = reinterpret_cast<const float4*>(v.feat + (((size_t)h * v.W + w) * v.Z + z) * 24);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float4 f = __ldg(p + j);
+      out[4 * j] = fmaf(wgt, f.x, out[4 * j]); out[4 * j + 1] = fmaf(wgt, f.y, out[4 * j + 1]);
+      out[4 * j + 2] = fmaf(wgt, f.z, out[4 * j + 2]); out[4 * j + 3] = fmaf(wgt, f.w, out[4 * j + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void scatter_feat24(const VolumeDev& V, float* __restrict__ gfeat, const Taps& t, const float g[24]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int dh = k >> 2, dw = (k >> 1) & 1, dz = k & 1;
+    float m = (dh ? t.mh1 : t.mh0) * (dw ? t.mw1 : t.mw0) * (dz ? t.mz1 : t.mz0);
+    if (m == 0.f) continue;
+    float wgt = (dh ? t.fh : 1.f - t.fh) * (dw ? t.fw : 1.f - t.fw) * (dz ? t.fz : 1.f - t.fz);
+    float4* p = reinterpret_cast<float4*>(gfeat + (((size_t)(t.h0 + dh) * V.W + (t.w0 + dw)) * V.Z + (t.z0 + dz)) * 24);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      atomicAdd(p + j, make_float4(wgt * g[4 * j], wgt * g[4 * j + 1], wgt * g[4 * j + 2], wgt * g[4 * j + 3]));   // red.global.add.v4.f32
+  }
+}
+
+__device__ __forceinline__ void colour_act(const RenderDev& P, const float f[3], float col[3], float raw[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    raw[c] = f[c] * kC0;
+    col[c] = P.sh_act == 0 ? fmaxf(raw[c] + 0.5f, 0.f) : sigmoidf_acc(raw[c]);
+  }
+}
+
 // FAST = affine metre->grid map, S a power of two (multiple of 32), cos-anneal finished, mid-point anchor: lean per-sample
 // path (closed-form jittered edges, interior gather chosen by a warp vote, base-2 alpha), ~2.4x fewer instructions.
-template <bool HAS_RGB, bool HAS_SEM, bool FAST>
-__global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+template <bool HAS_RGB, int SEM, bool FAST>
+__global__ void __launch_bounds__(128, SEM == 24 ? SO_TRAIN_FWD24_MIN_CTAS : SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                                const float* __restrict__ bkgd_rand, TrainOut O) {
+  constexpr bool HAS_SEM = SEM != 0;
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const int S = P.S;
@@ -141,9 +198,13 @@ __global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_k
     float carry = 1.0f, acc = 0.f, dsum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     float best = -INFINITY, best_ts = 0.f;
     int best_i = 0x7fffffff;
-    float sem_acc[HAS_SEM ? kMaxSem : 1];
-    if (HAS_SEM)
+    float sem_acc[SEM == 24 ? kSem24 : (HAS_SEM ? kMaxSem : 1)];
+    if (SEM == 24) {
+#pragma unroll
+      for (int c = 0; c < kSem24; ++c) sem_acc[c] = 0.f;
+    } else if (HAS_SEM) {
       for (int c = 0; c < kMaxSem; ++c) sem_acc[c] = 0.f;
+    }
     const float step = 1.0f / (float)S, span = c.tf - c.tn, k_log2 = P.inv_s * 1.4426950408889634f;
     // the jitter value of the NEXT chunk is requested one iteration ahead, so its DRAM latency is off the critical path
     float u_cur = (FAST && c.u) ? __ldg(c.u + lane) : 0.f;
@@ -206,12 +267,26 @@ __global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_k
         dsum = fmaf(w, q.mid, dsum);
         float cand = (dl < eps ? 0.f : w) * __fdividef(1.0f, fmaxf(dl, eps));  // neus_head.py:579-587
         if (cand > best) { best = cand; best_i = s; best_ts = ts; }
-        if (HAS_RGB) {
+        if (SEM == 24) {
+          float F[24], col[3], raw[3];
+          gather_feat24(V, q.t, F);
+          colour_act(P, F, col, raw);
+          cr = fmaf(w, col[0], cr); cg = fmaf(w, col[1], cg); cb = fmaf(w, col[2], cb);
+          float mx = F[3];
+#pragma unroll
+          for (int c = 1; c < kSem24; ++c) mx = fmaxf(mx, F[3 + c]);
+          float den = 0.f;
+#pragma unroll
+          for (int c = 0; c < kSem24; ++c) { F[3 + c] = expf(F[3 + c] - mx); den += F[3 + c]; }
+          float sc = w / den;
+#pragma unroll
+          for (int c = 0; c < kSem24; ++c) sem_acc[c] = fmaf(sc, F[3 + c], sem_acc[c]);
+        } else if (HAS_RGB) {
           float col[3], raw[3];
           sample_colour(V, P, q.t, col, raw);
           cr = fmaf(w, col[0], cr); cg = fmaf(w, col[1], cg); cb = fmaf(w, col[2], cb);
         }
-        if (HAS_SEM) {
+        if (SEM == 1) {
           float lg[kMaxSem];
           float mx = -INFINITY;
           for (int c = 0; c < n_sem; ++c) { float f1[1]; gather_feat<1>(V, q.t, 3 + c, f1); lg[c] = f1[0]; mx = fmaxf(mx, f1[0]); }
@@ -233,8 +308,12 @@ __global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_k
       if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_ts = ot; }
     }
     if (HAS_RGB) { cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); }
-    if (HAS_SEM)
+    if (SEM == 24) {
+#pragma unroll
+      for (int c = 0; c < kSem24; ++c) sem_acc[c] = warp_sum(sem_acc[c]);
+    } else if (HAS_SEM) {
       for (int c = 0; c < n_sem; ++c) sem_acc[c] = warp_sum(sem_acc[c]);
+    }
     if (lane == 0) {
       long long chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
       float lo = ws[2 * chunk], hi = ws[2 * chunk + 1];
@@ -252,8 +331,12 @@ __global__ void __launch_bounds__(128, SO_TRAIN_FWD_MIN_CTAS) render_train_fwd_k
         if (P.eval_clamp) { r = __saturatef(r); g = __saturatef(g); b = __saturatef(b); }
         O.rgb[3 * ray] = r; O.rgb[3 * ray + 1] = g; O.rgb[3 * ray + 2] = b;
       }
-      if (HAS_SEM && O.sem)
+      if (SEM == 24 && O.sem) {
+#pragma unroll
+        for (int c = 0; c < kSem24; ++c) O.sem[ray * kSem24 + c] = sem_acc[c];
+      } else if (HAS_SEM && O.sem) {
         for (int c = 0; c < n_sem; ++c) O.sem[ray * n_sem + c] = sem_acc[c];
+      }
     }
   }
 }
@@ -563,9 +646,10 @@ __device__ __forceinline__ void scatter_feat(const VolumeDev& V, float* __restri
   }
 }
 
-template <bool HAS_RGB, bool HAS_SEM>
-__global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
+template <bool HAS_RGB, int SEM>
+__global__ void __launch_bounds__(128, SEM == 24 ? SO_TRAIN_BWD24_MIN_CTAS : 1) render_train_bwd_kernel(VolumeDev V, RayDev R, RenderDev P, const float* __restrict__ ws,
                                                                const float* __restrict__ bkgd_rand, TrainGrad G) {
+  constexpr bool HAS_SEM = SEM != 0;
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const int S = P.S;
@@ -627,13 +711,29 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
       // dL/dw_s
       float Gw = (G.g_weights ? G.g_weights[oidx] : 0.f) + ga + gd * (q.mid - draw) / (acc + 1e-10f);
       float col[3] = {0.f, 0.f, 0.f}, raw[3] = {0.f, 0.f, 0.f};
-      float lg[HAS_SEM ? kMaxSem : 1];
+      float lg[SEM == 24 ? 24 : (HAS_SEM ? kMaxSem : 1)];      // SEM == 24: the 24 gathered channels, then [3..23] = softmax
       float gdot = 0.f;
-      if (HAS_RGB && G.g_rgb) {
+      if (SEM == 24) {
+        gather_feat24(V, q.t, lg);
+        colour_act(P, lg, col, raw);
+        if (G.g_rgb) Gw += gr[0] * (col[0] - bg[0]) + gr[1] * (col[1] - bg[1]) + gr[2] * (col[2] - bg[2]);
+        if (G.g_sem) {
+          float mx = lg[3];
+#pragma unroll
+          for (int c = 1; c < kSem24; ++c) mx = fmaxf(mx, lg[3 + c]);
+          float den = 0.f;
+#pragma unroll
+          for (int c = 0; c < kSem24; ++c) { lg[3 + c] = expf(lg[3 + c] - mx); den += lg[3 + c]; }
+          const float* gs = G.g_sem + ray * kSem24;
+#pragma unroll
+          for (int c = 0; c < kSem24; ++c) { lg[3 + c] /= den; gdot += __ldg(gs + c) * lg[3 + c]; }
+          Gw += gdot;
+        }
+      } else if (HAS_RGB && G.g_rgb) {
         sample_colour(V, P, q.t, col, raw);
         Gw += gr[0] * (col[0] - bg[0]) + gr[1] * (col[1] - bg[1]) + gr[2] * (col[2] - bg[2]);
       }
-      if (HAS_SEM && G.g_sem) {
+      if (SEM == 1 && G.g_sem) {
         float mx = -INFINITY;
         for (int c = 0; c < n_sem; ++c) { float f1[1]; gather_feat<1>(V, q.t, 3 + c, f1); lg[c] = f1[0]; mx = fmaxf(mx, f1[0]); }
         float den = 0.f;
@@ -666,7 +766,18 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
         if (G.g_eik) { ggx += G.g_eik[3 * oidx]; ggy += G.g_eik[3 * oidx + 1]; ggz += G.g_eik[3 * oidx + 2]; }
         // metre gradient (gx, gy, gz) = (dgw kw, dgh kh, dgd kd)
         scatter_sdf(V, G.g_vol_sdf, q.t, g_sdf, ggy * q.kh, ggx * q.kw, ggz * q.kd);
-        if (HAS_RGB && G.g_rgb && G.g_vol_feat) {
+        if (SEM == 24 && G.g_vol_feat && (G.g_rgb || G.g_sem)) {
+          // the gradient w.r.t. the 24 interpolated channels, built in place of the gathered values
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float dact = P.sh_act == 0 ? (raw[c] + 0.5f > 0.f ? 1.f : 0.f) : col[c] * (1.f - col[c]);
+            lg[c] = G.g_rgb ? w * gr[c] * dact * kC0 : 0.f;
+          }
+          const float* gs = G.g_sem + ray * kSem24;
+#pragma unroll
+          for (int c = 0; c < kSem24; ++c) lg[3 + c] = G.g_sem ? w * lg[3 + c] * (__ldg(gs + c) - gdot) : 0.f;
+          if (w != 0.f) scatter_feat24(V, G.g_vol_feat, q.t, lg);            // w == 0 (transmittance underflowed): every entry is 0
+        } else if (HAS_RGB && G.g_rgb && G.g_vol_feat) {
           float gf[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -675,7 +786,7 @@ __global__ void __launch_bounds__(128) render_train_bwd_kernel(VolumeDev V, RayD
           }
           scatter_feat<3>(V, G.g_vol_feat, q.t, 0, gf);
         }
-        if (HAS_SEM && G.g_sem && G.g_vol_feat) {
+        if (SEM == 1 && G.g_sem && G.g_vol_feat) {
           for (int c = 0; c < n_sem; ++c) {
             float gl[1] = {w * lg[c] * (G.g_sem[ray * n_sem + c] - gdot)};
             scatter_feat<1>(V, G.g_vol_feat, q.t, 3 + c, gl);
@@ -727,6 +838,9 @@ static int train_common_checks(const float* vol_sdf, const float* vol_feat, cons
 
 using namespace so;
 
+static bool g_force_sem_generic = false;
+// test hook: route 24-channel volumes through the generic (runtime channel count) semantic path
+extern "C" int so_render_train_force_sem_generic(int on) { g_force_sem_generic = on != 0; return SO_OK; }
 static bool g_force_fwd32 = false;
 // test hook: route so_render_train_forward through the one-ray-per-warp kernel even when the batched one applies
 extern "C" int so_render_train_force_fwd32(int on) { g_force_fwd32 = on != 0; return SO_OK; }
@@ -762,6 +876,7 @@ extern "C" int so_render_train_forward(const float* vol_sdf, const float* vol_fe
                     P.cos_anneal == 1.0f && P.anchor_mid;
   // batched-ray kernel (U chunks in flight, optional z-pair volume); the one-ray-per-warp kernel covers semantics,
   // non-affine mappings, S not a multiple of 32 U and the cos-anneal phase
+  const bool sem24 = want_sem && V.n_feat == 24 && V.feat_pitch == 24 && (reinterpret_cast<uintptr_t>(vol_feat) & 15) == 0 && !g_force_sem_generic;
   const bool v5 = fast && !want_sem && ((P.S >> 5) % SO_TRAIN_FWD5_U) == 0 && !g_force_fwd32;
 #define SO_TRAIN_FWD(RGB, SEM, F) render_train_fwd_kernel<RGB, SEM, F><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, O)
   if (v5) {
@@ -782,9 +897,10 @@ extern "C" int so_render_train_forward(const float* vol_sdf, const float* vol_fe
     else { if (vp) SO_TRAIN_FWD5_P(false, true); else SO_TRAIN_FWD5_P(false, false); }
 #undef SO_TRAIN_FWD5_P
 #undef SO_TRAIN_FWD5
-  } else if (want_sem) { if (fast) SO_TRAIN_FWD(true, true, true); else SO_TRAIN_FWD(true, true, false); }
-  else if (want_rgb) { if (fast) SO_TRAIN_FWD(true, false, true); else SO_TRAIN_FWD(true, false, false); }
-  else { if (fast) SO_TRAIN_FWD(false, false, true); else SO_TRAIN_FWD(false, false, false); }
+  } else if (want_sem && sem24) { if (fast) SO_TRAIN_FWD(true, 24, true); else SO_TRAIN_FWD(true, 24, false); }
+  else if (want_sem) { if (fast) SO_TRAIN_FWD(true, 1, true); else SO_TRAIN_FWD(true, 1, false); }
+  else if (want_rgb) { if (fast) SO_TRAIN_FWD(true, 0, true); else SO_TRAIN_FWD(true, 0, false); }
+  else { if (fast) SO_TRAIN_FWD(false, 0, true); else SO_TRAIN_FWD(false, 0, false); }
 #undef SO_TRAIN_FWD
   note_launch(1);
   return check_launch();
@@ -812,9 +928,12 @@ extern "C" int so_render_train_backward(const float* vol_sdf, const float* vol_f
   long long ctas = ceil_div64(R.ray_count, 4);
   unsigned grid = (unsigned)(ctas < (long long)kNumSMs * 16 ? ctas : (long long)kNumSMs * 16);
   ProfScope prof(7, st);
-  if (want_sem) render_train_bwd_kernel<true, true><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
-  else if (want_rgb) render_train_bwd_kernel<true, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
-  else render_train_bwd_kernel<false, false><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
+  const bool sem24 = V.n_feat == 24 && V.feat_pitch == 24 && (want_rgb || want_sem) && !g_force_sem_generic &&
+                     ((reinterpret_cast<uintptr_t>(vol_feat) | reinterpret_cast<uintptr_t>(g_vol_feat)) & 15) == 0;
+  if (sem24) render_train_bwd_kernel<true, 24><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
+  else if (want_sem) render_train_bwd_kernel<true, 1><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
+  else if (want_rgb) render_train_bwd_kernel<true, 0><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
+  else render_train_bwd_kernel<false, 0><<<grid, 128, 0, st>>>(V, R, P, workspace, bkgd_rand, G);
   note_launch(1);
   return check_launch();
 }

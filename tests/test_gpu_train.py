@@ -27,7 +27,8 @@ def _oracle_train(vol, mref, i2l, pix, aabb, inv_s, S, jitter, training, color_d
 
 
 @pytest.mark.parametrize('n_feat,S,use_jitter', [(0, 64, False), (0, 48, True), (7, 40, True),
-                                                 (0, 128, True), (0, 256, False), (3, 128, True)])   # power-of-two S >= 64: batched-ray kernel
+                                                 (0, 128, True), (0, 256, False), (3, 128, True),
+                                                 (24, 64, True), (24, 40, False)])   # 24: the vectorised rgb + 21-class path (nuscenes_occ.py:350)
 def test_render_train_forward_backward(n_feat, S, use_jitter):
     dev = _dev()
     from oracle.mapping import GridMeterMappingRef

@@ -439,45 +439,69 @@ def reference_style_gpu(dev, color_dims, our_launch_s, rays_per_frame):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def train_form_probe(dev, hbm_peak, iters=10):
+def train_form_probe(dev, hbm_peak, iters=10, cf=25, frames=1):
     """North-star side figure (SURVEY 8d caveat): the TRAINING-form render forward -- the kernel that must emit ~6 KB of
-    per-sample tensors per ray -- at BASELINE configs[4] sizes (6 cams x 48 x 100 rays x 256 samples, TPV 257x257x25,
-    Cf = 1), timed with the library's CUDA events (L2 flushed before every launch), against the measured HBM peak.
-    Same set-up as scripts/bench_train_render.py.  Untimed w.r.t. the bench step; reported next to `roofline`."""
+    per-sample tensors per ray -- at BASELINE configs[4] sizes (6 cams x 48 x 100 rays x 256 samples, TPV 257x257x25) with the
+    REAL head of config/nuscenes/nuscenes_occ.py:350 (color_dims = 24: Cf = 25 decoded channels, rgb + 21 semantic classes
+    rendered), timed with the library's CUDA events (L2 flushed before every launch), against the measured HBM peak.
+    Algorithmic bytes = SURVEY 8d's per-ray figure (28 + 16 + S * (weights 4 + ts 4 + deltas 4 + eik_grad 12) = 6 188 B/ray,
+    178 MB per step); the volume (sdf + 24 feature channels, 165 MB) and jitter reads are reported separately.  Same set-up as
+    scripts/bench_train_render.py; the Cf = 1 figure of round 1 is kept as `cf1`."""
     from selfocc_b200 import ops, synth, _lib
     from selfocc_b200.mapping import GridMeterMapping
     margs = dict(synth.NUSC_MAPPING, d_size=[24, 0], d_range=[-4.0, 4.0, 4.0])
     aabb = [-51.2, -51.2, -4.0, 51.2, 51.2, 4.0]
     m = GridMeterMapping(**margs)
-    desc = m.volume_desc(0)
-    vs = synth.pack_sdf_volume(synth.analytic_sdf_volume(m, noise=0.02), desc.zpitch).to(dev)
     _, i2l = synth.camera_rig()
-    i2l = torch.tensor(i2l, dtype=torch.float32, device=dev)
+    i2l = torch.tensor(i2l, dtype=torch.float32, device=dev).repeat(frames, 1, 1)
+    ncam = 6 * frames
     ny, nx, S = 48, 100, 256
-    n = 6 * ny * nx
-    jit = torch.rand(n, S + 1, device=dev)
-    invs = torch.tensor([20.0], device=dev)
-    want = ['depth', 'acc', 'fars', 'weights', 'ts', 'deltas', 'eik_grad']
-    cfg = dict(desc=desc, cam_mats=i2l, rays=ops.make_ray_desc(6, grid=(ny, nx, 16.0, 3.0, 16.0, 5.0)),
-               params=ops.make_render_params(aabb, S, 20.0, training=True, bkgd='white'), jitter=jit, bkgd_rand=None, want=want)
+    n = ncam * ny * nx
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    _lib.profile_enable(True)
-    with torch.no_grad():
-        for it in range(iters + 3):
-            if it == 3:
-                torch.cuda.synchronize()
-                _lib.profile_reset()
-            flush.zero_()
-            ops.RenderTrainFunction.apply(vs, None, invs, cfg)
-    torch.cuda.synchronize()
-    ms, calls = _lib.profile_read()['render_train_fwd']
-    fwd_ms = ms / calls
-    out_bytes = n * (S * (4 + 4 + 4 + 12) + 4 * 3)
-    in_bytes = n * (S + 1) * 4 + desc.H * desc.W * desc.zpitch * 4
-    gbs = (out_bytes + in_bytes) / (fwd_ms * 1e-3) / 1e9
-    return {'kernel': 'render_train_fwd5_kernel (+ zpair_pack_kernel)', 'workload': 'nuscenes_occ_train 6x48x100 rays x256, Cf=1',
-            'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak, 'launch_ms': fwd_ms,
-            'algorithmic_bytes_per_launch': out_bytes + in_bytes, 'rays_per_s': n / (fwd_ms * 1e-3)}
+
+    def run(cfv):
+        n_feat = cfv - 1
+        desc = m.volume_desc(n_feat)
+        vs = synth.pack_sdf_volume(synth.analytic_sdf_volume(m, noise=0.02), desc.zpitch).to(dev)
+        vf = (0.5 * torch.randn(desc.H, desc.W, desc.Z, desc.feat_pitch, device=dev)) if n_feat else None
+        jit = torch.rand(n, S + 1, device=dev)
+        bk = torch.rand(n, 3, device=dev) if n_feat else None
+        invs = torch.tensor([20.0], device=dev)
+        want = ['depth', 'acc', 'fars', 'weights', 'ts', 'deltas', 'eik_grad'] + (['rgb'] if n_feat >= 3 else []) + (['sem'] if n_feat > 3 else [])
+        cfg = dict(desc=desc, cam_mats=i2l, rays=ops.make_ray_desc(ncam, grid=(ny, nx, 16.0, 3.0, 16.0, 5.0)),
+                   params=ops.make_render_params(aabb, S, 20.0, training=True, bkgd='random' if n_feat else 'white'), jitter=jit,
+                   bkgd_rand=bk, want=want)
+        _lib.profile_enable(True)
+        with torch.no_grad():
+            for it in range(iters + 3):
+                if it == 3:
+                    torch.cuda.synchronize()
+                    _lib.profile_reset()
+                flush.zero_()
+                ops.RenderTrainFunction.apply(vs, vf, invs, cfg)
+        torch.cuda.synchronize()
+        ms, calls = _lib.profile_read()['render_train_fwd']
+        fwd_ms = ms / calls
+        per_ray = 28 + 16 + S * (4 + 4 + 4 + 12)
+        out_extra = n * ((12 if n_feat >= 3 else 0) + 4 * max(n_feat - 3, 0))
+        vol_bytes = desc.H * desc.W * desc.zpitch * 4 + (desc.H * desc.W * desc.Z * desc.feat_pitch * 4 if n_feat else 0)
+        jit_bytes = n * (S + 1) * 4
+        alg = n * per_ray + out_extra
+        gbs = alg / (fwd_ms * 1e-3) / 1e9
+        return {'launch_ms': fwd_ms, 'algorithmic_bytes_per_launch': alg, 'achieved': gbs, 'frac': gbs / hbm_peak,
+                'volume_bytes': vol_bytes, 'jitter_bytes': jit_bytes,
+                'frac_incl_volume_and_jitter': (alg + vol_bytes + jit_bytes) / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
+                'rays_per_s': n / (fwd_ms * 1e-3)}
+    main = run(cf)
+    out = {'kernel': 'render_train_fwd_kernel<RGB, SEM=24> (one ray per warp, lane = sample)' if cf == 25 else 'render_train_fwd5_kernel',
+           'workload': 'nuscenes_occ_train %dx48x100 rays x256, Cf=%d (config/nuscenes/nuscenes_occ.py:350)' % (ncam, cf),
+           'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s', 'bytes_per_ray': 28 + 16 + S * 24}
+    out.update(main)
+    if cf != 1:
+        c1 = run(1)
+        out['cf1'] = {k: c1[k] for k in ('launch_ms', 'achieved', 'frac', 'frac_incl_volume_and_jitter', 'rays_per_s')}
+        out['cf1']['kernel'] = 'render_train_fwd5_kernel (+ zpair_pack_kernel), depth-only head'
+    return out
 
 
 def parity_probe(model, feats, metas, workload, dev, color_dims, stride=50):

@@ -270,6 +270,12 @@ int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const
 int so_layer_norm(const float* x, const float* add, const float* gamma, const float* beta, float* y, int64_t rows,
                   int32_t C, float eps, void* stream);
 
+/* A3  one FPN level into the flattened token tensor (tpvformer_encoder.py:261-277): feat [N, C, hw] ->
+ * out[n, level_start + p, :] = (feat[n, :, p] + cams_embeds[n, :]) + level_embed[:], out being [N, total, C].  Replaces
+ * flatten(3).permute(...) + the two embedding adds + torch.cat over levels + .contiguous() (five passes over 59 MB). */
+int so_flatten_level(const float* feat, const float* cams_embeds, const float* level_embed, float* out, int32_t N, int32_t C,
+                     int32_t hw, int64_t level_start, int64_t total, void* stream);
+
 /* A4  projection of pillar reference points into the cameras.  Replaces point_sampling
  * (model/encoder/bevformer/utils.py:116-206, no post_rots / focal_ratios branch).
  *   ref_3d [D, Q, 3] metres, lidar2img [N, 4, 4], img_h/img_w = metas[0]['img_shape']
@@ -305,6 +311,10 @@ int so_tpv_cross_attn_forward_strided(const float* value, const int64_t* spatial
                                       const float* offsets, const float* logits, const float* uv, const uint8_t* vis,
                                       float* slots, int32_t* count, int32_t N, int32_t Nv, int32_t Hd, int32_t Dh, int32_t Q,
                                       int32_t L, int32_t D, int32_t value_ld, int32_t offsets_ld, int32_t logits_ld, void* stream);
+
+/* Test hook: 1 = run so_tpv_cross_attn_forward* / so_tpv_self_attn_forward* on the first-generation kernels (every lane of
+ * a (query, head) redoes the sample set-up) instead of the shared-set-up kernels.  Both are parity-tested. */
+int so_attn_force_v1(int on);
 
 /* A5  visible-query index lists, as the reference builds them with nonzero()
  * (image_cross_attention.py:90-94), without a host sync: for each camera, ascending int64 query

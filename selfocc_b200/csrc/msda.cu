@@ -304,6 +304,173 @@ __global__ void __launch_bounds__(256, SO_SELF_ATTN_MIN_CTAS) tpv_self_attn_kern
   if (live) *reinterpret_cast<float4*>(out + item * DH + lc * 4) = acc;
 }
 
+// ======================================================================================================================
+// v2 of the two fused attention cores: the per-sample set-up is computed ONCE per (query, head, sample) instead of once
+// per lane.  In the kernels above the DH/4 lanes of an item each redo the whole set-up of every sample (location
+// arithmetic, floor, bounds, 4 bilinear weights, softmax weight: ~70 of the ~116 instructions per sample, plus three
+// parameter loads and spill traffic under the register cap; ncu r1: l1tex 83 %, issue 65 %).  Here the LANES lanes of an
+// item set up LANES DIFFERENT samples of a round (lane j: point d0 + j), park the result -- 4 corner weights already
+// multiplied by the attention weight and by the zero-padding mask, and the 4 (clamped, always in-bounds) absolute pixel
+// indices -- in 32 bytes of shared memory, and then each 4-lane sub-group walks over its 4 samples of the round reading
+// the parked set-up with two broadcast LDS.128 and issuing the 4 coalesced 64-byte corner reads + 16 FMAs.  Same
+// arithmetic per sample as bilinear4 (weights are the same products; the attention weight is folded in before the
+// corner sum instead of after), so results agree to rounding with the v1 kernels (tests: both vs the fp64 oracle).
+struct SamplePark { float w[4]; int p[4]; };     // 32 B
+
+// set-up of one bilinear sample at normalised (lx, ly) of a level [Hl, Wl] whose first pixel has absolute index `base`
+__device__ __forceinline__ SamplePark park_sample(float lx, float ly, int Hl, int Wl, int base, float aw) {
+  SamplePark s;
+  float x = lx * (float)Wl - 0.5f, y = ly * (float)Hl - 0.5f;
+  const bool inside = y > -1.f && x > -1.f && y < (float)Hl && x < (float)Wl;
+  float xf = floorf(x), yf = floorf(y);
+  int x0 = (int)xf, y0 = (int)yf;
+  float fx = x - xf, fy = y - yf;
+  const bool xa = x0 >= 0, xb = x0 + 1 < Wl, ya = y0 >= 0, yb = y0 + 1 < Hl;
+  const float a = inside ? aw : 0.f;
+  s.w[0] = (ya && xa) ? a * ((1.f - fy) * (1.f - fx)) : 0.f;
+  s.w[1] = (ya && xb) ? a * ((1.f - fy) * fx) : 0.f;
+  s.w[2] = (yb && xa) ? a * (fy * (1.f - fx)) : 0.f;
+  s.w[3] = (yb && xb) ? a * (fy * fx) : 0.f;
+  // clamped indices: a masked corner re-reads a valid pixel with weight 0 (no predicated loads, no out-of-bounds address)
+  int xc0 = min(max(x0, 0), Wl - 1), xc1 = min(max(x0 + 1, 0), Wl - 1);
+  int yc0 = min(max(y0, 0), Hl - 1), yc1 = min(max(y0 + 1, 0), Hl - 1);
+  if (!inside) { xc0 = xc1 = yc0 = yc1 = 0; }
+  s.p[0] = base + yc0 * Wl + xc0; s.p[1] = base + yc0 * Wl + xc1;
+  s.p[2] = base + yc1 * Wl + xc0; s.p[3] = base + yc1 * Wl + xc1;
+  return s;
+}
+
+__device__ __forceinline__ void consume_sample(const SamplePark* __restrict__ sp, const float* __restrict__ vlane, int value_ld, float4& acc) {
+  const float4 w = *reinterpret_cast<const float4*>(sp->w);
+  const int4 p = *reinterpret_cast<const int4*>(sp->p);
+  if (w.x == 0.f && w.y == 0.f && w.z == 0.f && w.w == 0.f) return;       // uniform over the 4 lanes of the sub-group
+  const float4 v0 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.x * value_ld));
+  const float4 v1 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.y * value_ld));
+  const float4 v2 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.z * value_ld));
+  const float4 v3 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.w * value_ld));
+  acc.x = fmaf(w.x, v0.x, acc.x); acc.y = fmaf(w.x, v0.y, acc.y); acc.z = fmaf(w.x, v0.z, acc.z); acc.w = fmaf(w.x, v0.w, acc.w);
+  acc.x = fmaf(w.y, v1.x, acc.x); acc.y = fmaf(w.y, v1.y, acc.y); acc.z = fmaf(w.y, v1.z, acc.z); acc.w = fmaf(w.y, v1.w, acc.w);
+  acc.x = fmaf(w.z, v2.x, acc.x); acc.y = fmaf(w.z, v2.y, acc.y); acc.z = fmaf(w.z, v2.z, acc.z); acc.w = fmaf(w.z, v2.w, acc.w);
+  acc.x = fmaf(w.w, v3.x, acc.x); acc.y = fmaf(w.w, v3.y, acc.y); acc.z = fmaf(w.w, v3.z, acc.z); acc.w = fmaf(w.w, v3.w, acc.w);
+}
+
+#ifndef SO_ATTN2_MIN_CTAS
+#define SO_ATTN2_MIN_CTAS 4
+#endif
+
+// DH = 16 only (4 lanes x float4).  Requires D % (4 * SPLIT) == 0 (every round lies inside one level of one camera).
+template <int SPLIT>
+__global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_cross_attn2_kernel(
+    const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+    const float* __restrict__ offsets, const float* __restrict__ logits, const float* __restrict__ uv,
+    const unsigned char* __restrict__ vis, float* __restrict__ slots, int* __restrict__ count, int N, int Nv, int Hd, int Q, int L,
+    int D, int value_ld, int off_ld, int lg_ld) {
+  constexpr int DH = 16, LPI = 4, LANES = LPI * SPLIT;
+  __shared__ Levels lv;
+  __shared__ __align__(16) SamplePark park[256];
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LANES;
+  const int li = (int)(t % LANES);
+  const int lc = li % LPI, sg = li / LPI;
+  const long long n_items = (long long)Q * Hd;
+  const bool live = item < n_items;
+  if (!live) item = n_items - 1;
+  const int h = (int)(item % Hd);
+  const int q = (int)(item / Hd);
+  const int LD = L * D;
+  const float* op = offsets + (long long)q * off_ld + (long long)h * LD * 2;
+  const float* lg = logits + (long long)q * lg_ld + (long long)h * LD;
+  float mx, inv_sum;
+  softmax_stats<LANES>(lg, LD, li, mx, inv_sum);
+  const float* vlane = value + h * DH + lc * 4;
+  SamplePark* mine = park + threadIdx.x;
+  const SamplePark* grp = park + (threadIdx.x - li) + sg * LPI;          // the 4 samples this sub-group consumes per round
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int cam = 0; cam < N; ++cam) {
+    const bool visible = __ldg(vis + (long long)cam * Q + q) != 0;       // image_cross_attention.py:92 (query visible in cam)
+    if (!__any_sync(0xffffffffu, visible)) continue;
+    cnt += visible ? 1 : 0;
+    const float* uvp = uv + ((long long)cam * Q + q) * D * 2;
+    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < L; ++l) {
+      const int Hl = lv.h[l], Wl = lv.w[l];
+      const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
+      const int base = cam * Nv + (int)lv.start[l];
+      for (int d0 = 0; d0 < D; d0 += LANES) {
+        const int d = d0 + li;
+        const float2 r = __ldg(reinterpret_cast<const float2*>(uvp) + d);
+        const float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * D + d);
+        const float aw = visible ? __expf(__ldg(lg + l * D + d) - mx) * inv_sum : 0.f;
+        // image_cross_attention.py:326-328: ref + offset / (w_l, h_l)   (reciprocal multiply: <= 1 ulp from the division)
+        *mine = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < LPI; ++j) consume_sample(grp + j, vlane, value_ld, part);
+        __syncwarp();
+      }
+    }
+    acc.x += part.x; acc.y += part.y; acc.z += part.z; acc.w += part.w;  // :129-131, camera order
+  }
+#pragma unroll
+  for (int s2 = LPI; s2 < LANES; s2 <<= 1) {   // fold the sample groups
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s2);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, s2); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, s2);
+  }
+  if (!live || sg != 0) return;
+  float c = (float)max(cnt, 1);  // :133-136
+  acc.x /= c; acc.y /= c; acc.z /= c; acc.w /= c;
+  *reinterpret_cast<float4*>(slots + item * DH + lc * 4) = acc;
+  if (count && h == 0 && lc == 0) count[q] = cnt;
+}
+
+// self-attention (cross-view hybrid), DH = 16, P % 4 == 0
+__global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_self_attn2_kernel(
+    const float* __restrict__ value, const long long* __restrict__ shapes, const long long* __restrict__ lsi,
+    const float* __restrict__ offsets, const float* __restrict__ logits, const float* __restrict__ ref, float* __restrict__ out, int Nv,
+    int Hd, int Q, int L, int P, int value_ld, int off_ld, int lg_ld) {
+  constexpr int DH = 16, LPI = 4;
+  __shared__ Levels lv;
+  __shared__ __align__(16) SamplePark park[256];
+  load_levels(lv, shapes, lsi, L);
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long item = t / LPI;
+  const int lc = (int)(t % LPI);
+  const long long n_items = (long long)Q * Hd;
+  const bool live = item < n_items;
+  if (!live) item = n_items - 1;
+  const int h = (int)(item % Hd);
+  const int q = (int)(item / Hd);
+  const int LP = L * P;
+  const float* op = offsets + (long long)q * off_ld + (long long)h * LP * 2;
+  const float* lg = logits + (long long)q * lg_ld + (long long)h * LP;
+  const float* rp = ref + (long long)q * LP * 2;
+  float mx, inv_sum;
+  softmax_stats<LPI>(lg, LP, lc, mx, inv_sum);
+  const float* vlane = value + h * DH + lc * 4;
+  SamplePark* mine = park + threadIdx.x;
+  const SamplePark* grp = park + (threadIdx.x - lc);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const int Hl = lv.h[l], Wl = lv.w[l];
+    const float rw = 1.0f / (float)Wl, rh = 1.0f / (float)Hl;
+    const int base = (int)lv.start[l];
+    for (int p0 = 0; p0 < P; p0 += LPI) {
+      const int p = p0 + lc;
+      const float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l * P + p);
+      const float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * P + p);
+      const float aw = __expf(__ldg(lg + l * P + p) - mx) * inv_sum;
+      *mine = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);    // cross_view_hybrid_attention.py:97-99
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < LPI; ++j) consume_sample(grp + j, vlane, value_ld, acc);
+      __syncwarp();
+    }
+  }
+  if (live) *reinterpret_cast<float4*>(out + item * DH + lc * 4) = acc;
+}
+
 // ---- A4 point_sampling (bevformer/utils.py:116-206) ---------------------------------------------------------
 // One thread per (camera, query, pillar point): fully coalesced uv / mask stores.  The projection uses plain fp32
 // mul/add in a fixed left-to-right order (no FMA contraction): `mask` generates index lists.  `vis` (any over the
@@ -384,6 +551,10 @@ using namespace so;
     else return SO_ERR_UNSUPPORTED;        \
   } while (0)
 
+static bool g_attn_force_v1 = false;
+// Test hook: 1 = route the fused attention cores through the first-generation kernels (one set-up per lane).
+extern "C" int so_attn_force_v1(int on) { g_attn_force_v1 = on != 0; return SO_OK; }
+
 extern "C" int so_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                                const float* loc, const float* weights, float* out, int32_t B, int32_t Nv, int32_t Hd,
                                int32_t Dh, int32_t Nq, int32_t L, int32_t P, void* stream) {
@@ -459,6 +630,13 @@ extern "C" int so_tpv_cross_attn_forward_strided(const float* value, const int64
   long long threads = (long long)Q * Hd * (Dh / 4) * split;
   unsigned grid = (unsigned)ceil_div64(threads, 256);
   ProfScope prof(2, st);
+#define SO_CROSS2(SP) tpv_cross_attn2_kernel<SP><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D, value_ld, offsets_ld, logits_ld)
+  if (Dh == 16 && D % (4 * split) == 0 && !g_attn_force_v1 && (long long)N * Nv < (1LL << 31)) {
+    if (split == 4) SO_CROSS2(4); else if (split == 2) SO_CROSS2(2); else SO_CROSS2(1);
+    note_launch(1);
+    return check_launch();
+  }
+#undef SO_CROSS2
 #define SO_CROSS(DHV, SP) tpv_cross_attn_kernel<DHV, SP><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, uv, vis, slots, count, N, Nv, Hd, Q, L, D, value_ld, offsets_ld, logits_ld)
   if (Dh == 16) { if (split == 4) SO_CROSS(16, 4); else if (split == 2) SO_CROSS(16, 2); else SO_CROSS(16, 1); }
   else if (Dh == 32) { if (split == 4) SO_CROSS(32, 4); else if (split == 2) SO_CROSS(32, 2); else SO_CROSS(32, 1); }
@@ -491,6 +669,11 @@ extern "C" int so_tpv_self_attn_forward_strided(const float* value, const int64_
   long long threads = (long long)Q * Hd * (Dh / 4);
   unsigned grid = (unsigned)ceil_div64(threads, 256);
   ProfScope prof(3, st);
+  if (Dh == 16 && P % 4 == 0 && !g_attn_force_v1) {
+    tpv_self_attn2_kernel<<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P, value_ld, offsets_ld, logits_ld);
+    note_launch(1);
+    return check_launch();
+  }
   SO_DISPATCH_DH(Dh, (tpv_self_attn_kernel<16><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P, value_ld, offsets_ld, logits_ld)),
                  (tpv_self_attn_kernel<32><<<grid, 256, 0, st>>>(value, shp, lsi, offsets, logits, ref, out, Nv, Hd, Q, L, P, value_ld, offsets_ld, logits_ld)));
   note_launch(1);

@@ -60,3 +60,42 @@ extern "C" int so_layer_norm(const float* x, const float* add, const float* gamm
   note_launch(1);
   return check_launch();
 }
+
+// ---- A3: FPN level -> token rows (tpvformer_encoder.py:261-277) ------------------------------------------------------
+// feat [N, C, hw] of one level -> out[n, level_start + p, :] = (feat[n, :, p] + cams_embeds[n, :]) + level_embed[:]
+// (the reference's two adds in its order), i.e. flatten(3).permute + both embeddings + the concat over levels in ONE pass:
+// a 32 x 32 shared-memory tile transpose, coalesced on both sides.  HBM-bound: 2 x N x hw x C x 4 bytes per level.
+namespace so {
+__global__ void __launch_bounds__(256) flatten_level_kernel(const float* __restrict__ feat, const float* __restrict__ cams,
+                                                            const float* __restrict__ lvl, float* __restrict__ out, int C, int hw,
+                                                            long long level_start, long long total) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+  const float* src = feat + (long long)n * C * hw;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = c0 + ty + 8 * j, p = p0 + tx;
+    if (c < C && p < hw) tile[ty + 8 * j][tx] = src[(long long)c * hw + p];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int p = p0 + ty + 8 * j, c = c0 + tx;
+    if (c < C && p < hw)
+      out[((long long)n * total + level_start + p) * C + c] = __fadd_rn(__fadd_rn(tile[tx][ty + 8 * j], __ldg(cams + n * C + c)), __ldg(lvl + c));
+  }
+}
+}  // namespace so
+
+extern "C" int so_flatten_level(const float* feat, const float* cams_embeds, const float* level_embed, float* out, int32_t N,
+                                int32_t C, int32_t hw, int64_t level_start, int64_t total, void* stream) {
+  if (!feat || !cams_embeds || !level_embed || !out || N < 1 || C < 1 || hw < 1 || level_start < 0 || level_start + hw > total)
+    return SO_ERR_INVALID_ARG;
+  if (N > 65535 || (C + 31) / 32 > 65535) return SO_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+  so::flatten_level_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, cams_embeds, level_embed, out, C, hw, level_start, total);
+  so::note_launch(1);
+  return so::check_launch();
+}

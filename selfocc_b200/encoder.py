@@ -648,6 +648,18 @@ class TPVFormerEncoder(nn.Module):
 
     def flatten_features(self, img_feats):
         """A3: [B,N,C,h,w] x L -> [N, sum(hw), B, C] with camera + level embeddings (tpvformer_encoder.py:261-277)."""
+        f0 = img_feats[0]
+        if f0.is_cuda and f0.dtype == torch.float32 and f0.shape[0] == 1 and all(f.is_contiguous() for f in img_feats) \
+                and not _needs_grad(self.cams_embeds, *img_feats):
+            shapes = tuple((f.shape[3], f.shape[4]) for f in img_feats)  # fused transposing pass (so_flatten_level)
+            key = (shapes, f0.device)
+            if getattr(self, '_shape_key', None) != key:                 # the two tiny int64 tables are per-resolution constants
+                spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=f0.device)
+                level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+                self._shape_key, self._shape_val = key, (spatial_shapes, level_start_index)
+            spatial_shapes, level_start_index = self._shape_val
+            return ops.flatten_levels(img_feats, self.cams_embeds.detach().contiguous(), self.level_embeds.detach().contiguous()), \
+                spatial_shapes, level_start_index
         feats, shapes = [], []
         for lvl, feat in enumerate(img_feats):
             bs, num_cam, c, h, w = feat.shape

@@ -459,6 +459,24 @@ def linear_supported(K, N=None):
     return K in (96, 192) and (N is None or N % 4 == 0)
 
 
+def flatten_levels(img_feats, cams_embeds, level_embeds):
+    """A3: [1, N, C, h, w] x L -> [N, sum(hw), 1, C] with camera + level embeddings, one transposing pass per level."""
+    lib = _lib.load()
+    N, Cc = img_feats[0].shape[1], img_feats[0].shape[2]
+    hws = [f.shape[3] * f.shape[4] for f in img_feats]
+    total = sum(hws)
+    out = torch.empty(N, total, 1, Cc, device=img_feats[0].device, dtype=torch.float32)
+    _chk(cams_embeds, name='cams_embeds'); _chk(level_embeds, name='level_embeds')
+    start = 0
+    for l, f in enumerate(img_feats):
+        assert f.shape[0] == 1 and f.shape[1] == N and f.shape[2] == Cc
+        _chk(f, name='img_feats[%d]' % l)
+        _lib.check(lib.so_flatten_level(_p(f), _p(cams_embeds), _p(level_embeds[l]), _p(out), N, Cc, hws[l], start, total, _stream()),
+                   'so_flatten_level')
+        start += hws[l]
+    return out
+
+
 def layer_norm(x, gamma, beta, eps=1e-5, add=None):
     """y = LayerNorm(x [+ add]) over the last dim (fp32), one warp per row."""
     lib = _lib.load()

@@ -139,14 +139,25 @@ def test_fused_cross_attention_core_matches_rebatch_reference():
         err = (slots.cpu() - slots_ref).abs().max().item()
         print('cross-attn core max abs err %.3e' % err)
         assert err < 5e-5
+        # the two kernel generations (shared set-up, D % (4 * groups) == 0, vs one set-up per lane) state the same function
+        from selfocc_b200 import _lib
+        _lib.load().so_attn_force_v1(1)
+        try:
+            slots1, count1 = ops.tpv_cross_attn_forward(feat[:, :, 0].reshape(N, Nv, Hd, C // Hd).contiguous().to(dev), ss, lsi,
+                                                        off.view(Q, Hd, len(shapes), D, 2).contiguous().to(dev),
+                                                        lg.view(Q, Hd, len(shapes), D).contiguous().to(dev), uv, vis, want_count=True)
+        finally:
+            _lib.load().so_attn_force_v1(0)
+        assert torch.allclose(slots1, slots, atol=2e-5) and torch.equal(count1, count)
 
 
-def test_fused_self_attention_core():
+@pytest.mark.parametrize('P', [5, 12])       # 12 (every shipped config): the shared-set-up kernel; 5: the per-lane kernel
+def test_fused_self_attention_core(P):
     dev = _dev()
     from oracle import lifting as ol
     from selfocc_b200 import ops
     g = torch.Generator().manual_seed(9)
-    C, Hd, P = 96, 6, 5
+    C, Hd = 96, 6
     H, W, Z = 9, 7, 4
     shapes = [(H, W), (Z, H), (W, Z)]
     Q = H * W + Z * H + W * Z
@@ -166,3 +177,33 @@ def test_fused_self_attention_core():
     err = (out.cpu() - core_ref).abs().max().item()
     print('self-attn core max abs err %.3e' % err)
     assert err < 5e-5
+    # the two kernel generations state the same function
+    from selfocc_b200 import _lib
+    _lib.load().so_attn_force_v1(1)
+    try:
+        out1 = ops.tpv_self_attn_forward(query[0].view(Q, Hd, C // Hd).contiguous().to(dev), ss, lsi, off.contiguous().to(dev),
+                                         lg.contiguous().to(dev), ref2d.contiguous().to(dev))
+    finally:
+        _lib.load().so_attn_force_v1(0)
+    assert torch.allclose(out1, out, atol=2e-5)
+
+
+def test_fused_flatten_equals_the_reference_sequence():
+    """A3 (tpvformer_encoder.py:261-277): so_flatten_level == flatten(3).permute + cams_embeds + level_embeds + cat, bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    dev = torch.device('cuda:0')
+    from selfocc_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N, C = 6, 96
+    shapes = [(12, 25), (6, 13), (3, 7), (2, 3)]
+    feats = [torch.randn(1, N, C, h, w, generator=g).to(dev) for h, w in shapes]
+    cams, lvls = torch.randn(N, C, generator=g).to(dev), torch.randn(4, C, generator=g).to(dev)
+    ref = []
+    for l, f in enumerate(feats):
+        t = f.flatten(3).permute(1, 0, 3, 2)
+        t = t + cams[:, None, None, :]
+        ref.append(t + lvls[None, None, l:l + 1, :])
+    ref = torch.cat(ref, 2).permute(0, 2, 1, 3).contiguous()
+    got = ops.flatten_levels(feats, cams, lvls)
+    assert got.shape == ref.shape and torch.equal(got, ref)

@@ -564,7 +564,9 @@ def cpu_reference(workload, steps, warmup, color_dims=3):
     from oracle.mapping import GridMeterMappingRef
     from oracle import lifting as ol, render as orender, rays as orays
     from selfocc_b200 import synth
-    torch.set_num_threads(os.cpu_count())
+    # 32 OpenMP threads: on the shared 128-core hosts of this pool 128 threads spin against the other tenants and the same
+    # sample took 0.28 s .. 11.3 s from run to run (BENCH_r01, profiles/r2_bench_v1_rgb.json); `cores` reports what is used
+    torch.set_num_threads(min(32, os.cpu_count()))
     w = WORKLOADS[workload]
     feats, metas, shapes = make_frame(workload, seed=100)
     mref = GridMeterMappingRef(**synth.NUSC_MAPPING)
@@ -615,7 +617,7 @@ def cpu_reference(workload, steps, warmup, color_dims=3):
     ts = sorted(render_sample() for _ in range(max(steps, 1)))
     t_r = ts[len(ts) // 2]
     frame_s = t_lift + t_decode + t_r * scale
-    return {'value': rays_per_frame / frame_s, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+    return {'value': rays_per_frame / frame_s, 'unit': 'rays/s', 'cores': torch.get_num_threads(), 'host_cores': os.cpu_count(), 'kind': 'port',
             'sample': 'oracle port (reference not installable), before CUDA init: 1 encoder layer on a 65x65x9 lattice (%.2fs) scaled x%.1f '
                       'queries x4 layers + decode of %d/%d h-rows (%.2fs) scaled + render of 1 cam x %dx%d rays x 256 samples '
                       '(median %.3fs of %d, min %.3f max %.3f) scaled x%.0f to %d rays, color_dims=%d'

@@ -25,6 +25,14 @@ def forward_train(head, representation, metas=None, jitter=None, bkgd_rand=None,
     sampler = head._sampler()
     grid = sampler.draw()
     rays = sampler.table(grid)
+    shard = getattr(head, 'ray_shard', None)
+    if shard is not None and shard[1] > 1:
+        # ray-sharded training (BASELINE configs[4]): rank r renders the r-th contiguous slice of EVERY camera's pixel rays, so the
+        # per-camera output lists the losses consume keep their structure (fewer rays per camera); with every rank on the same
+        # frame and the loss a mean over rays, averaging the parameter gradients over ranks (DDP) gives the full-batch gradient
+        from .dist import ray_slice
+        b, c = ray_slice(rays.shape[0], shard[1], shard[0])
+        rays, grid = rays[b:b + c].contiguous(), None
     M = head.img2lidar.matrices(metas, dev)
     bs, num_cams = M.shape[:2]
     assert bs == 1, 'only support bs = 1 currently'

@@ -39,3 +39,34 @@ def test_all_gather_rays_gloo_world2():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(60) for p in procs]
     assert res == [(0, True, (total, 2)), (1, True, (total, 2))]
+
+
+def test_sharded_lifter_slices_round_trip():
+    """Host logic of the query-sharded lifting (selfocc_b200/dist.py:ShardedLifter): per-plane contiguous slices, padding to the
+    common per-rank length, and the reassembly of what all_gather_into_tensor delivers -- on the CPU, no kernels involved."""
+    from selfocc_b200 import synth, configs
+    from selfocc_b200.registry import build_head
+    import selfocc_b200.segmentor  # noqa: F401
+    from selfocc_b200.dist import ShardedLifter
+    margs, rng = synth.small_mapping(6, 3)
+    cfg = configs.hot_path_config(mapping_args=margs, pc_range=rng, num_cams=3, num_layers=1, num_points_cross=(4, 4, 4),
+                                  num_points_self=4, num_samples=32, ray_number=(6, 10), ray_img_size=(90, 160))
+    enc = build_head(cfg).encoder
+    sl = ShardedLifter(enc)
+    H, W, Z = enc.tpv_size
+    assert sl.sizes == [H * W, Z * H, W * Z]
+    q = torch.randn(sum(sl.sizes), 8)
+    for world in (1, 2, 3, 5, 8):
+        bufs = []
+        covered = torch.zeros(sum(sl.sizes), dtype=torch.int32)
+        for r in range(world):
+            local = sl._local_rows(q, r, world)
+            assert local.shape[0] == sum(c for _, c in sl.slices(r, world))
+            bufs.append(sl.pad_local(local, r, world))
+            off = 0
+            for (b, c), n in zip(sl.slices(r, world), sl.sizes):
+                covered[off + b:off + b + c] += 1
+                off += n
+        assert (covered == 1).all()                               # every query owned by exactly one rank
+        assert all(b.shape[0] == sl.per_rank_rows(world) for b in bufs)
+        assert torch.equal(sl.assemble(torch.stack(bufs, 0), world), q)

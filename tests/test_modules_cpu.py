@@ -221,3 +221,29 @@ def test_head_checkpoint_key_map():
         alt[k2] = v
     missing, unexpected = m3.load_state_dict(alt, strict=False)
     assert not missing and not unexpected
+
+
+def test_masked_median_and_metric_assembly_cpu():
+    """Host side of the device DepthMetric (selfocc_b200/metric.py): the sort-based masked LOWER median equals
+    torch.median(x[mask]) (utils/metric_util.py:331-333), and sums -> metrics is cal_depth_metric's arithmetic."""
+    from selfocc_b200.metric import masked_median, metrics_from_sums
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(5, 101, generator=g) * 50
+    mask = torch.rand(5, 101, generator=g) < 0.6
+    mask[3] = False
+    mask[3, 7] = True                                              # a single valid element
+    mask[4, :] = True
+    ref = torch.stack([torch.median(x[i][mask[i]]) for i in range(5)])
+    assert torch.equal(masked_median(x, mask), ref)
+    gt, pred = torch.rand(3, 40, generator=g) * 60 + 1, torch.rand(3, 40, generator=g) * 60 + 1
+    d = gt - pred
+    th = torch.maximum(gt / pred, pred / gt)
+    sums = torch.stack([(d.abs() / gt).sum(1), (d * d / gt).sum(1), (d * d).sum(1), ((gt.log() - pred.log()) ** 2).sum(1),
+                        (th < 1.25).float().sum(1), (th < 1.25 ** 2).float().sum(1), (th < 1.25 ** 3).float().sum(1),
+                        torch.full((3,), 40.0)], 1)
+    m = metrics_from_sums(sums)
+    from oracle.metric import cal_depth_metric_ref
+    for i in range(3):
+        r = cal_depth_metric_ref(pred[i], gt[i])
+        for k in ('abs_rel', 'sq_rel', 'rmse', 'rmse_log', 'a1', 'a2', 'a3'):
+            assert torch.allclose(m[k][i], r[k].float(), rtol=1e-5, atol=1e-7), k

@@ -268,8 +268,9 @@ def test_render_poses_equals_separate_renders_and_novel_view_matches_oracle():
     ref = orender.head_render_ref(vol, mref, origin.double(), direction.double(), rng, float(f.deviation_network.get_variance()),
                                   S=64, color_dims=3, bkgd='white')
     d, dref = out['ms_depths'][0].cpu().double(), ref['depth']
-    assert (((d - dref).abs() / dref.abs().clamp_min(1e-6)) > 1e-4).float().mean() < 0.01     # cell-face flips only (oracle/parity.py)
-    assert torch.allclose(out['ms_colors'][0].cpu().double(), ref['rgb'], atol=1e-3)
+    good = ((d - dref).abs() / dref.abs().clamp_min(1e-6)) <= 1e-4
+    assert good.float().mean() > 0.99                               # the rest: fp32 cell-face flips (oracle/parity.py)
+    assert torch.allclose(out['ms_colors'][0].cpu().double()[good], ref['rgb'][good], atol=1e-4)
 
 
 def test_device_depth_metric_matches_reference_arithmetic():

@@ -315,7 +315,13 @@ __global__ void __launch_bounds__(256, SO_SELF_ATTN_MIN_CTAS) tpv_self_attn_kern
 // the parked set-up with two broadcast LDS.128 and issuing the 4 coalesced 64-byte corner reads + 16 FMAs.  Same
 // arithmetic per sample as bilinear4 (weights are the same products; the attention weight is folded in before the
 // corner sum instead of after), so results agree to rounding with the v1 kernels (tests: both vs the fp64 oracle).
-struct SamplePark { float w[4]; int p[4]; };     // 32 B
+struct SamplePark { float w[4]; int p[4]; };     // 32 B: parked as one float4 + one int4 in two shared arrays
+// Slot layout inside a warp's 32 entries (conflict-free on both sides): the lane L = 4 g + j that sets sample j of sub-group
+// g up writes slot j * 8 + g; at step j the 8 sub-groups read slots j * 8 + 0..7 = 128 contiguous bytes (one wavefront; the
+// first version parked array-of-structs at a 128-byte stride between sub-groups: 8-way bank conflicts, ncu counted more
+// shared-memory wavefronts than global ones, profiles/r2_attn2_ncu.txt).
+__device__ __forceinline__ int park_write_slot(int lane) { return (lane & 3) * 8 + (lane >> 2); }
+__device__ __forceinline__ int park_read_slot(int lane, int j) { return j * 8 + (lane >> 2); }
 
 // set-up of one bilinear sample at normalised (lx, ly) of a level [Hl, Wl] whose first pixel has absolute index `base`
 __device__ __forceinline__ SamplePark park_sample(float lx, float ly, int Hl, int Wl, int base, float aw) {
@@ -340,9 +346,7 @@ __device__ __forceinline__ SamplePark park_sample(float lx, float ly, int Hl, in
   return s;
 }
 
-__device__ __forceinline__ void consume_sample(const SamplePark* __restrict__ sp, const float* __restrict__ vlane, int value_ld, float4& acc) {
-  const float4 w = *reinterpret_cast<const float4*>(sp->w);
-  const int4 p = *reinterpret_cast<const int4*>(sp->p);
+__device__ __forceinline__ void consume_sample(const float4 w, const int4 p, const float* __restrict__ vlane, int value_ld, float4& acc) {
   if (w.x == 0.f && w.y == 0.f && w.z == 0.f && w.w == 0.f) return;       // uniform over the 4 lanes of the sub-group
   const float4 v0 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.x * value_ld));
   const float4 v1 = __ldg(reinterpret_cast<const float4*>(vlane + (long long)p.y * value_ld));
@@ -367,7 +371,8 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_cross_attn2_kernel
     int D, int value_ld, int off_ld, int lg_ld) {
   constexpr int DH = 16, LPI = 4, LANES = LPI * SPLIT;
   __shared__ Levels lv;
-  __shared__ __align__(16) SamplePark park[256];
+  __shared__ float4 park_w[256];
+  __shared__ int4 park_p[256];
   load_levels(lv, shapes, lsi, L);
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long item = t / LANES;
@@ -384,8 +389,8 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_cross_attn2_kernel
   float mx, inv_sum;
   softmax_stats<LANES>(lg, LD, li, mx, inv_sum);
   const float* vlane = value + h * DH + lc * 4;
-  SamplePark* mine = park + threadIdx.x;
-  const SamplePark* grp = park + (threadIdx.x - li) + sg * LPI;          // the 4 samples this sub-group consumes per round
+  const int wbase = threadIdx.x & ~31, wl = threadIdx.x & 31;
+  const int slot_w = wbase + park_write_slot(wl);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   for (int cam = 0; cam < N; ++cam) {
@@ -404,10 +409,15 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_cross_attn2_kernel
         const float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * D + d);
         const float aw = visible ? __expf(__ldg(lg + l * D + d) - mx) * inv_sum : 0.f;
         // image_cross_attention.py:326-328: ref + offset / (w_l, h_l)   (reciprocal multiply: <= 1 ulp from the division)
-        *mine = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);
+        const SamplePark sp = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);
+        park_w[slot_w] = make_float4(sp.w[0], sp.w[1], sp.w[2], sp.w[3]);
+        park_p[slot_w] = make_int4(sp.p[0], sp.p[1], sp.p[2], sp.p[3]);
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < LPI; ++j) consume_sample(grp + j, vlane, value_ld, part);
+        for (int j = 0; j < LPI; ++j) {
+          const int rs = wbase + park_read_slot(wl, j);
+          consume_sample(park_w[rs], park_p[rs], vlane, value_ld, part);
+        }
         __syncwarp();
       }
     }
@@ -432,7 +442,8 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_self_attn2_kernel(
     int Hd, int Q, int L, int P, int value_ld, int off_ld, int lg_ld) {
   constexpr int DH = 16, LPI = 4;
   __shared__ Levels lv;
-  __shared__ __align__(16) SamplePark park[256];
+  __shared__ float4 park_w[256];
+  __shared__ int4 park_p[256];
   load_levels(lv, shapes, lsi, L);
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long item = t / LPI;
@@ -449,8 +460,8 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_self_attn2_kernel(
   float mx, inv_sum;
   softmax_stats<LPI>(lg, LP, lc, mx, inv_sum);
   const float* vlane = value + h * DH + lc * 4;
-  SamplePark* mine = park + threadIdx.x;
-  const SamplePark* grp = park + (threadIdx.x - lc);
+  const int wbase = threadIdx.x & ~31, wl = threadIdx.x & 31;
+  const int slot_w = wbase + park_write_slot(wl);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 0; l < L; ++l) {
     const int Hl = lv.h[l], Wl = lv.w[l];
@@ -461,10 +472,15 @@ __global__ void __launch_bounds__(256, SO_ATTN2_MIN_CTAS) tpv_self_attn2_kernel(
       const float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l * P + p);
       const float2 o = __ldg(reinterpret_cast<const float2*>(op) + l * P + p);
       const float aw = __expf(__ldg(lg + l * P + p) - mx) * inv_sum;
-      *mine = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);    // cross_view_hybrid_attention.py:97-99
+      const SamplePark sp = park_sample(fmaf(o.x, rw, r.x), fmaf(o.y, rh, r.y), Hl, Wl, base, aw);    // cross_view_hybrid_attention.py:97-99
+      park_w[slot_w] = make_float4(sp.w[0], sp.w[1], sp.w[2], sp.w[3]);
+      park_p[slot_w] = make_int4(sp.p[0], sp.p[1], sp.p[2], sp.p[3]);
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < LPI; ++j) consume_sample(grp + j, vlane, value_ld, acc);
+      for (int j = 0; j < LPI; ++j) {
+        const int rs = wbase + park_read_slot(wl, j);
+        consume_sample(park_w[rs], park_p[rs], vlane, value_ld, acc);
+      }
       __syncwarp();
     }
   }

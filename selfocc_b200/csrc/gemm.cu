@@ -78,6 +78,7 @@ constexpr int kMaxStages = 4;
 
 struct PipeCfg {
   int BN, KA, stages;       // n-tile width, atoms along K (K / 32), ring depth
+  int epi_bufs;             // TMA-store staging tiles per epilogue warp (2 when shared memory allows: store i overlaps staging i+1)
   int w_bytes;              // resident W bytes = 2 * KA * BN * 128
   int smem;                 // dynamic shared memory request (incl. 1 KB alignment slack)
 };
@@ -87,8 +88,14 @@ static PipeCfg make_pipe_cfg(int N, int K) {
   c.BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
   c.KA = K / kAtomK;
   c.w_bytes = 2 * c.KA * c.BN * 128;
-  const int fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
-  const int budget = 227 * 1024 - 1024 - fixed;
+  c.epi_bufs = 2;
+  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 4 + 256;
+  int budget = 227 * 1024 - 1024 - fixed;
+  if (budget / kStageBytes < 3) {            // K = 192: the resident W tile leaves no room; keep the deeper load ring
+    c.epi_bufs = 1;
+    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
+    budget = 227 * 1024 - 1024 - fixed;
+  }
   c.stages = budget / kStageBytes;
   if (c.stages > kMaxStages) c.stages = kMaxStages;
   c.smem = fixed + c.stages * kStageBytes + 1024;
@@ -100,15 +107,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                           const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_y,
                           const float* __restrict__ bias, const float* __restrict__ residual, long long M, int N, int BN, int KA,
-                          int stages, int n_tiles, int m_tiles, int relu) {
+                          int stages, int n_tiles, int m_tiles, int relu, int epi_bufs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_bytes = 2 * KA * BN * 128;
   uint8_t* w_hi = sm;
   uint8_t* w_lo = sm + KA * BN * 128;
   uint8_t* ring = sm + w_bytes;                                   // stages x [hi 16 KB | lo 16 KB], 1 KB aligned
-  uint8_t* epi = ring + stages * kStageBytes;                     // 4 x 4 KB, 1 KB aligned (swizzle atoms)
-  float* bias_s = reinterpret_cast<float*>(epi + 4 * kEpiWarpBytes);
+  uint8_t* epi = ring + stages * kStageBytes;                     // 4 x epi_bufs x 4 KB, 1 KB aligned (swizzle atoms)
+  float* bias_s = reinterpret_cast<float*>(epi + 4 * epi_bufs * kEpiWarpBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kMaxBN);
   uint64_t* w_full = bars;
   uint64_t* full = bars + 1;
@@ -224,7 +231,8 @@ linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
   } else if (warp >= 8) {
     // ===== epilogue: TMEM -> registers (+bias, ReLU, +residual) -> swizzled smem tile -> TMA store =====
     const int q = warp & 3;                              // TMEM lane quarter of this warp
-    uint8_t* tile = epi + q * kEpiWarpBytes;
+    uint8_t* tile0 = epi + q * epi_bufs * kEpiWarpBytes;
+    int ebuf = 0;
     for (int i = tid - 256; i < BN; i += 128) bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
     int acc = 0; uint32_t acc_ph = 0;
@@ -235,7 +243,11 @@ linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), r);
-        if (lane == 0) tma_store_wait_read();             // previous TMA store has finished reading the tile
+        uint8_t* tile = tile0 + ebuf * kEpiWarpBytes;
+        if (lane == 0) {                                  // the store that last used THIS staging tile has finished reading it
+          if (epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read();
+        }
+        if (epi_bufs == 2) ebuf ^= 1;
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -452,7 +464,7 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
   if (groups > m_tiles) groups = m_tiles;
   ProfScope prof(8, st);
   linear_3xtf32_pipe_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
-                                                                            cfg.KA, cfg.stages, n_tiles, m_tiles, relu);
+                                                                            cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs);
   note_launch(1);
   return check_launch();
 }

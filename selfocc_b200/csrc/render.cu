@@ -45,21 +45,45 @@ __global__ void __launch_bounds__(256) bounds_kernel(RayDev R, RenderDev P, floa
     mx = __fmul_rn(__fadd_rn(eL, eE), 0.5f);
     chunk = R.chunk_len > 0 ? gid / R.chunk_len : 0;
   }
-  // warp-aggregate when the whole warp sits in one chunk (the common case)
+  // aggregate per warp, then per CTA, when everybody sits in one chunk (the common case): ONE atomic pair per CTA.
+  // (One pair per warp -- 270 k same-address atomics for 8.64 M rays -- made this pre-pass 165 us, ncu r2_launches.)
   unsigned full = __activemask();
   long long c0 = __shfl_sync(full, chunk, 0);
   bool uniform = __all_sync(full, (!ok) || chunk == c0);
+  __shared__ float s_mn[8], s_mx[8];
+  __shared__ long long s_chunk[8];
+  __shared__ int s_uniform;
+  if (threadIdx.x == 0) s_uniform = 1;
+  __syncthreads();
   if (uniform) {
     for (int s = 16; s > 0; s >>= 1) {
       mn = fminf(mn, __shfl_xor_sync(full, mn, s));
       mx = fmaxf(mx, __shfl_xor_sync(full, mx, s));
     }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_mn[w] = mn; s_mx[w] = mx; s_chunk[w] = c0; }
+  if (!uniform) atomicAnd(&s_uniform, 0);
+  __syncthreads();
+  bool cta_uniform = s_uniform != 0;
+  if (cta_uniform) {
+    for (int i = 1; i < 8; ++i) cta_uniform = cta_uniform && (s_chunk[i] == s_chunk[0] || s_mn[i] == INFINITY);
+  }
+  if (cta_uniform) {
+    if (threadIdx.x == 0) {
+      float bmn = s_mn[0], bmx = s_mx[0];
+      long long bc = s_chunk[0];
+      for (int i = 1; i < 8; ++i) { if (s_mn[i] != INFINITY) bc = s_chunk[i]; bmn = fminf(bmn, s_mn[i]); bmx = fmaxf(bmx, s_mx[i]); }
+      if (bmn != INFINITY) {
+        // all values are >= 0, so the int ordering equals the float ordering
+        atomicMin((int*)(ws + 2 * bc), __float_as_int(bmn));
+        atomicMax((int*)(ws + 2 * bc + 1), __float_as_int(bmx));
+      }
+    }
+  } else if (uniform) {
     if ((threadIdx.x & 31) == 0 && mn != INFINITY) {
-      // all values are >= 0, so the int ordering equals the float ordering.  Same-address atomics serialise in L2
-      // (~1 ns each): issue one only when it can still improve the current bound (monotone, so the race is benign).
-      volatile float* vw = ws;
-      if (mn < vw[2 * c0]) atomicMin((int*)(ws + 2 * c0), __float_as_int(mn));
-      if (mx > vw[2 * c0 + 1]) atomicMax((int*)(ws + 2 * c0 + 1), __float_as_int(mx));
+      atomicMin((int*)(ws + 2 * c0), __float_as_int(mn));
+      atomicMax((int*)(ws + 2 * c0 + 1), __float_as_int(mx));
     }
   } else if (ok) {
     atomicMin((int*)(ws + 2 * chunk), __float_as_int(mn));

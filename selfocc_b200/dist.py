@@ -130,7 +130,8 @@ class ShardedLifter:
         feat, shapes, lsi = enc.flatten_features(ms_img_feats)
         dev = feat.device
         uvs, masks, vises = enc.project_reference_points(metas, dev)
-        pos = torch.cat([p for p in enc._tpv_pos()], 0)                       # [Q_total, C]
+        pv = enc._tpv_pos()
+        pos = enc._pos_cat[0] if getattr(enc, '_pos_val', None) is pv else torch.cat(list(pv), 0)      # [Q_total, C]
         return dict(feat=feat, shapes=shapes, lsi=lsi, uvs=uvs, vises=vises, pos=pos,
                     ref=enc.cross_view_ref_points)                            # [Q_total, 3, P, 2]
 

@@ -682,12 +682,18 @@ class TPVFormerEncoder(nn.Module):
         key = tuple((w._version, w.data_ptr()) for w in ws)
         if getattr(self, '_pos_key', None) != key:
             with torch.no_grad():
-                self._pos_key, self._pos_val = key, pe()
+                vals = pe()
+                self._pos_key, self._pos_val = key, vals
+                self._pos_cat = torch.cat(vals, 0).unsqueeze(0)      # [1, Q_hw + Q_zh + Q_wz, C]: what every layer concatenates
         return self._pos_val
 
     def forward(self, representation, ms_img_feats=None, metas=None, **kwargs):
         bs = ms_img_feats[0].shape[0]
-        tpv_pos = [p.unsqueeze(0).repeat(bs, 1, 1) if bs > 1 else p.unsqueeze(0) for p in self._tpv_pos()]
+        pos = self._tpv_pos()
+        if bs == 1 and getattr(self, '_pos_val', None) is pos:
+            tpv_pos = self._pos_cat                               # cached concatenation (the layers accept a tensor): no 31 MB cat per layer
+        else:
+            tpv_pos = [p.unsqueeze(0).repeat(bs, 1, 1) if bs > 1 else p.unsqueeze(0) for p in pos]
         feat_flatten, spatial_shapes, level_start_index = self.flatten_features(ms_img_feats)
         tpv_embed = self.forward_layers(representation, feat_flatten, feat_flatten, tpv_pos=tpv_pos,
                                         spatial_shapes=spatial_shapes, level_start_index=level_start_index, img_metas=metas)

@@ -188,11 +188,11 @@ def run_b200(args):
         `gather_join` at the end of the timed region, so every gather is paid for inside the region)."""
         if world == 1:
             return out['ms_depths'][0]
-        cols = [out['ms_depths'][0].reshape(-1, 1), out['ms_max_depths'][0].reshape(-1, 1)]
+        cols = [out['ms_depths'][0].reshape(-1), out['ms_max_depths'][0].reshape(-1)]
         if has_rgb:
-            cols.append(out['ms_colors'][0].reshape(-1, 3))
-        local = torch.cat(cols, -1)
-        full = local.new_empty((world * rays_per_frame, local.shape[1]))
+            cols.append(out['ms_colors'][0].reshape(-1))
+        local = torch.cat(cols)                                        # planar pack: contiguous copies (an interleaved [R, 5] pack
+        full = local.new_empty(world * local.numel())                  # is a strided write of every column, ~1 ms per frame)
         gather_join()                                                  # frame k-1's gather must be done before frame k's starts
         pending.append((dist.all_gather_into_tensor(full, local, async_op=True), (full, local)))
         return full

@@ -3,7 +3,7 @@ import os
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-from selfocc_b200.dist import ray_slice, all_gather_rays
+from selfocc_b200.dist import ray_slice, all_gather_rays, all_gather_planar
 
 
 def test_ray_slice_equals_torch_chunk():
@@ -25,6 +25,11 @@ def _worker(rank, world, port, total, q):
     local = torch.stack([torch.arange(b, b + c, dtype=torch.float32), -torch.arange(b, b + c, dtype=torch.float32)], -1)
     full = all_gather_rays(local, total)
     ok = torch.equal(full[:, 0], torch.arange(total, dtype=torch.float32)) and torch.equal(full[:, 1], -full[:, 0])
+    # planar multi-tensor gather: a [count] and a [count, 3] tensor in one collective
+    d = torch.arange(b, b + c, dtype=torch.float32)
+    rgb = torch.stack([d, 2 * d, 3 * d], -1)
+    fd, frgb = all_gather_planar([d, rgb], total)
+    ok = ok and torch.equal(fd, torch.arange(total, dtype=torch.float32)) and torch.equal(frgb[:, 2], 3 * fd) and frgb.shape == (total, 3)
     q.put((rank, bool(ok), tuple(full.shape)))
     dist.barrier()
     dist.destroy_process_group()

@@ -80,7 +80,15 @@ with torch.no_grad():
     sdf1 = model.head.forward_occ(res['representation'], aabb=rng, resolution=0.5)['sdf']
     got = frame_sharded(model, feats, metas)
     sdfN, _ = uniform_sdf_sharded(model.head, rng, 0.5)
-ok = torch.equal(got['depth'], one['ms_depths'][0].reshape(-1)) and torch.equal(got['max_depth'], one['ms_max_depths'][0].reshape(-1)) \
+    # the same frame replayed from a CUDA graph (kernels + NCCL captured per rank): device-tensor metas, static inputs
+    from selfocc_b200.dist import GraphedFrame
+    metas_d = [dict(lidar2img=torch.tensor(np.asarray(metas[0]['lidar2img']), dtype=torch.float32, device=dev),
+                    img2lidar=torch.tensor(np.asarray(metas[0]['img2lidar']), dtype=torch.float32, device=dev), img_shape=metas[0]['img_shape'])]
+    gf = GraphedFrame(model, feats, metas_d)
+    rep = {k: v.clone() for k, v in gf.replay().items()}
+    rep2 = gf.replay()
+ok = all(torch.equal(rep[k], got[k]) and torch.equal(rep2[k], got[k]) for k in got)
+ok = ok and torch.equal(got['depth'], one['ms_depths'][0].reshape(-1)) and torch.equal(got['max_depth'], one['ms_max_depths'][0].reshape(-1)) \
     and torch.equal(got['acc'], one['ms_accs'][0].reshape(-1)) and torch.equal(got['rgb'], one['ms_colors'][0].reshape(-1, 3)) \
     and torch.equal(sdfN, sdf1)
 flag = torch.tensor([int(ok)], device=dev)
@@ -101,3 +109,33 @@ def test_frame_sharded_and_lattice_sharded_over_nccl(tmp_path):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n), '--master-addr',
                         '127.0.0.1', '--master-port', '29741', str(script)], capture_output=True, text=True, timeout=900)
     assert 'DIST_OK %d' % n in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_graphed_frame_single_gpu_equals_eager():
+    """GraphedFrame at world size 1 (no collectives): replaying the captured frame reproduces the eager result bit for bit and
+    follows the static input buffers."""
+    from selfocc_b200.dist import GraphedFrame, frame_sharded
+    import numpy as np
+    model, cfg, margs, rng, metas, feats, l2i, i2l = _setup(color_dims=3)
+    dev = torch.device('cuda:0')
+    model.to(dev)
+    model.head.num_samples = 64
+    model.head.render_bkgd = 'white'
+    feats = [f.to(dev) for f in feats]
+    metas_d = [dict(lidar2img=torch.tensor(np.asarray(metas[0]['lidar2img']), dtype=torch.float32, device=dev),
+                    img2lidar=torch.tensor(np.asarray(metas[0]['img2lidar']), dtype=torch.float32, device=dev), img_shape=metas[0]['img_shape'])]
+    with torch.no_grad():
+        eager = frame_sharded(model, feats, metas_d)
+        gf = GraphedFrame(model, feats, metas_d)
+        rep = gf.replay()
+        torch.cuda.synchronize()
+        for k in eager:
+            assert torch.equal(rep[k], eager[k]), k
+        for f in feats:                                  # new frame through the same static buffers
+            f.mul_(0.5)
+        eager2 = frame_sharded(model, feats, metas_d)
+        rep2 = gf.replay()
+        torch.cuda.synchronize()
+        for k in eager2:
+            assert torch.equal(rep2[k], eager2[k]), k
+        assert not torch.equal(eager2['depth'], eager['depth'])

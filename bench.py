@@ -52,6 +52,7 @@ def parse():
                     help='3: the configs[2] head (nuscenes_novel_depth.py:326); 0: depth-only head (nuscenes_depth.py)')
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='strong mode: issue the sharded frame eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--graph', action='store_true', help='strong mode at N > 1: capture the NCCL collectives into the graph too (opt-in)')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling (one frame sharded over the ranks) measurement')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='which measurement is the headline `value`')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-style eager-PyTorch-on-GPU side figure')
@@ -264,7 +265,7 @@ def run_b200(args):
         from selfocc_b200.dist import GraphedFrame
         s_eager_ms, _, _ = timed(lambda: frame_sharded(model, feats_0, metas_d, lifter=sl), K, W)
         step_strong, mode_s = None, 'eager issue'
-        if not args.no_graph:
+        if (world == 1 and not args.no_graph) or args.graph:   # NCCL inside a captured graph is opt-in: see GraphedFrame's docstring
             try:
                 gf = GraphedFrame(model, feats_0, metas_d, lifter=sl)
                 ok, why = 1, ''

@@ -261,6 +261,9 @@ int so_msda_backward(const float* value, const int64_t* spatial_shapes, const in
  * cross_view_hybrid_attention.py:79-86,118, tpvformer_encoder_layer.py:198-206).  w_hi / w_lo = so_split_tf32(w)
  * (w_hi = w with the low 13 mantissa bits cleared, w_lo = w - w_hi), computed once per weight.  K % 96 == 0;
  * x, w_hi, w_lo 16-byte aligned; relu: 0/1; bias / residual may be NULL. */
+/* Test hook: 1 = so_linear_3xtf32 with both MMA operands in shared memory (SS, the round-1 pipeline); 0 (default) = the X
+ * operand split into tensor memory (TS).  Both are parity-tested. */
+int so_linear_force_ss(int on);
 int so_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* stream);
 int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);

@@ -83,6 +83,27 @@ struct PipeCfg {
   int smem;                 // dynamic shared memory request (incl. 1 KB alignment slack)
 };
 
+// TS variant: a stage is the raw X atom only (16 KB); at most 4 stages (TMEM holds 4 x (hi | lo) x 32 columns next to the
+// two accumulators)
+static PipeCfg make_pipe_cfg_ts(int N, int K) {
+  PipeCfg c;
+  c.BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
+  c.KA = K / kAtomK;
+  c.w_bytes = 2 * c.KA * c.BN * 128;
+  c.epi_bufs = 2;
+  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 4 + 256;
+  int budget = 227 * 1024 - 1024 - fixed;
+  if (budget / kAtomBytesA < 3) {
+    c.epi_bufs = 1;
+    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
+    budget = 227 * 1024 - 1024 - fixed;
+  }
+  c.stages = budget / kAtomBytesA;
+  if (c.stages > kMaxStages) c.stages = kMaxStages;
+  c.smem = fixed + c.stages * kAtomBytesA + 1024;
+  return c;
+}
+
 static PipeCfg make_pipe_cfg(int N, int K) {
   PipeCfg c;
   c.BN = (N % 128 == 0) ? 128 : (N % 96 == 0 ? 96 : (N % 112 == 0 ? 112 : (N <= 128 ? ((N + 15) / 16) * 16 : 128)));
@@ -285,6 +306,201 @@ linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TS variant of the pipeline: the A operand (X split into hi / lo) lives in TENSOR MEMORY instead of shared memory.
+// Why: with both operands in shared memory every one of the 12 MMAs of an atom re-reads a 4 KB A slice and a 4 KB B slice,
+// and the converters write hi and lo back to shared memory: ~180 KB of shared-memory traffic per 16 KB atom = ~1 400
+// cycles at 128 B/clk against 768 cycles of tensor-core time -- the SS pipeline is shared-memory-bandwidth bound
+// (ncu: tensor pipe <= 11 %).  With A in TMEM the MMAs read only B from shared memory and the converters write to TMEM
+// (tcgen05.st, 256 B/clk): ~100 KB per atom.  TMEM: columns [0, 256) two accumulators, [256, 512) 4 stages x (hi | lo) x 32.
+__global__ void __launch_bounds__(kPipeThreads, 1)
+linear_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                          const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_y,
+                          const float* __restrict__ bias, const float* __restrict__ residual, long long M, int N, int BN, int KA,
+                          int stages, int n_tiles, int m_tiles, int relu, int epi_bufs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_bytes = 2 * KA * BN * 128;
+  uint8_t* w_hi = sm;
+  uint8_t* w_lo = sm + KA * BN * 128;
+  uint8_t* ring = sm + w_bytes;                                   // stages x raw X atom (16 KB), 1 KB aligned
+  uint8_t* epi = ring + stages * kAtomBytesA;                     // 4 x epi_bufs x 4 KB, 1 KB aligned (swizzle atoms)
+  float* bias_s = reinterpret_cast<float*>(epi + 4 * epi_bufs * kEpiWarpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kMaxBN);
+  uint64_t* w_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* conv = full + kMaxStages;
+  uint64_t* empty = conv + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int group = blockIdx.x / n_tiles, n_groups = gridDim.x / n_tiles;
+  const int n0 = n_tile * BN;
+
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);          // [0, 256): two accumulators; [256, 512): stages x (A hi | A lo) x 32 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)w_bytes);
+      for (int a = 0; a < KA; ++a) {
+        tma_load_2d(w_hi + a * BN * 128, &map_whi, a * kAtomK, n0, w_full);
+        tma_load_2d(w_lo + a * BN * 128, &map_wlo, a * kAtomK, n0, w_full);
+      }
+      int s = 0; uint32_t ph = 0;
+      constexpr int kPrefetchTiles = 4;                 // X tiles requested into L2 ahead of the smem ring
+      for (int p = 0; p < kPrefetchTiles; ++p) {
+        int mt = group + p * n_groups;
+        if (mt < m_tiles)
+          for (int a = 0; a < KA; ++a) tma_prefetch_l2_2d(&map_x, a * kAtomK, mt * kBM);
+      }
+      for (int mt = group; mt < m_tiles; mt += n_groups) {
+        const int mt_pf = mt + kPrefetchTiles * n_groups;
+        if (mt_pf < m_tiles)
+          for (int a = 0; a < KA; ++a) tma_prefetch_l2_2d(&map_x, a * kAtomK, mt_pf * kBM);
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, (uint32_t)kAtomBytesA);
+          tma_load_2d(ring + s * kAtomBytesA, &map_x, a * kAtomK, mt * kBM, full + s);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      mbar_wait(w_full, 0);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo);
+      for (int mt = group; mt < m_tiles; mt += n_groups) {
+        mbar_wait(tmem_empty + acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        uint32_t accum = 0;
+        for (int a = 0; a < KA; ++a) {
+          mbar_wait(conv + s, ph);
+          tc_fence_after();
+          const uint32_t ahi = tmem_base + 256u + (uint32_t)(s * 64), alo = ahi + 32u;     // A operand in tensor memory
+          const uint32_t bhi = whi + a * BN * 128, blo = wlo + a * BN * 128;
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const uint32_t ab = prod == 1 ? alo : ahi;
+            const uint32_t bb = prod == 2 ? blo : bhi;
+#pragma unroll
+            for (int k = 0; k < kAtomK / 8; ++k) {
+              umma_tf32_ts(d_tmem, ab + (uint32_t)(k * 8), make_desc(bb + k * 32), idesc, accum);
+              accum = 1u;
+            }
+          }
+          umma_commit(empty + s);                       // stage reusable once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tmem_full + acc);                   // accumulator complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== converters: X = hi + lo, written into TENSOR MEMORY (the A operand of the MMAs) =====
+    // warp w owns TMEM lanes 32 (w & 3) .. + 31 = tile rows; thread = one row: its 32 k-values are one 128-byte swizzled
+    // shared-memory row (chunk j lives at j ^ (row & 7)); hi and lo go to 32 TMEM columns each with tcgen05.st.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int s = 0; uint32_t ph = 0;
+    for (int mt = group; mt < m_tiles; mt += n_groups) {
+      for (int a = 0; a < KA; ++a) {
+        mbar_wait(full + s, ph);
+        const uint8_t* src = ring + s * kAtomBytesA + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+          float h;
+          h = tf32_rn(v.x); hi[4 * j] = __float_as_uint(h); lo[4 * j] = __float_as_uint(v.x - h);
+          h = tf32_rn(v.y); hi[4 * j + 1] = __float_as_uint(h); lo[4 * j + 1] = __float_as_uint(v.y - h);
+          h = tf32_rn(v.z); hi[4 * j + 2] = __float_as_uint(h); lo[4 * j + 2] = __float_as_uint(v.z - h);
+          h = tf32_rn(v.w); hi[4 * j + 3] = __float_as_uint(h); lo[4 * j + 3] = __float_as_uint(v.w - h);
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(s * 64);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(conv + s);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: TMEM -> registers (+bias, ReLU, +residual) -> swizzled smem tile -> TMA store =====
+    const int q = warp & 3;                              // TMEM lane quarter of this warp
+    uint8_t* tile0 = epi + q * epi_bufs * kEpiWarpBytes;
+    int ebuf = 0;
+    for (int i = tid - 256; i < BN; i += 128) bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int mt = group; mt < m_tiles; mt += n_groups) {
+      mbar_wait(tmem_full + acc, acc_ph);
+      tc_fence_after();
+      const long long gr = (long long)mt * kBM + q * 32 + lane;      // this thread's output row
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), r);
+        uint8_t* tile = tile0 + ebuf * kEpiWarpBytes;
+        if (lane == 0) {                                  // the store that last used THIS staging tile has finished reading it
+          if (epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read();
+        }
+        if (epi_bufs == 2) ebuf ^= 1;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+          float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
+                                 __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (residual) {
+            const int gc = n0 + c0 + 4 * j;
+            if (gr < M && gc + 3 < N) {
+              float4 rr = __ldg(reinterpret_cast<const float4*>(residual + gr * N + gc));
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            } else if (gr < M) {
+              if (gc < N) v.x += __ldg(residual + gr * N + gc);
+              if (gc + 1 < N) v.y += __ldg(residual + gr * N + gc + 1);
+              if (gc + 2 < N) v.z += __ldg(residual + gr * N + gc + 2);
+            }
+          }
+          // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        // TMA clips rows >= M and columns >= N; chunks that start beyond this n-tile's width are skipped
+        if (lane == 0 && n0 + c0 < N) tma_store_2d(&map_y, tile, n0 + c0, mt * kBM + q * 32);
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_3xtf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                      const __grid_constant__ CUtensorMap map_wlo, const float* __restrict__ bias,
@@ -426,6 +642,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
 
 using namespace so;
 
+static bool g_linear_force_ss = false;
+// Test hook: 1 = both MMA operands from shared memory (the round-1 pipeline); 0 (default) = A operand in tensor memory.
+extern "C" int so_linear_force_ss(int on) { g_linear_force_ss = on != 0; return SO_OK; }
+
 extern "C" int so_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   if (!w || !hi || !lo || n < 0) return SO_ERR_INVALID_ARG;
   if (n == 0) return SO_OK;
@@ -442,7 +662,8 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
     return SO_ERR_INVALID_ARG;                                                    // TMA needs 16-byte aligned bases
   if (M == 0) return SO_OK;
   if (M > 0x7fffffffLL) return SO_ERR_UNSUPPORTED;
-  PipeCfg cfg = make_pipe_cfg(N, K);
+  const bool ts = !g_linear_force_ss;
+  PipeCfg cfg = ts ? make_pipe_cfg_ts(N, K) : make_pipe_cfg(N, K);
   if (cfg.stages < 2) return SO_ERR_UNSUPPORTED;
   CUtensorMap mx, mhi, mlo;
   int rc;
@@ -454,7 +675,9 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
   if ((rc = make_tmap(&my, y, M, N, 32))) return rc;                                 // store box: 32 rows x 32 floats
   static PerDeviceOnce smem_attr;
   if ((rc = smem_attr.run([] {
-         return check_cuda(cudaFuncSetAttribute(linear_3xtf32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+         int r = check_cuda(cudaFuncSetAttribute(linear_3xtf32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+         if (r) return r;
+         return check_cuda(cudaFuncSetAttribute(linear_3xtf32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
        })))
     return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -463,8 +686,12 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
   ProfScope prof(8, st);
-  linear_3xtf32_pipe_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
+  if (ts)
+    linear_3xtf32_ts_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
                                                                             cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs);
+  else
+    linear_3xtf32_pipe_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
+                                                                              cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs);
   note_launch(1);
   return check_launch();
 }

@@ -318,7 +318,10 @@ class GraphedFrame:
     ranks a sharded frame is ~4 ms of GPU work behind ~110 python-issued launches and 7 collectives, i.e. host-bound when run
     eagerly.  Inputs are static device buffers (copy the frame's FPN features / camera matrices into ``feats`` / ``metas``'
     tensors before ``replay()``); outputs are the static tensors ``self.out``.  ``metas`` must hold DEVICE tensors (a numpy
-    matrix list would be uploaded from pageable memory inside the capture)."""
+    matrix list would be uploaded from pageable memory inside the capture).
+    STATUS: validated at world size 1 (tests/test_gpu_dist.py, bit-identical to eager).  With torch.distributed's NCCL
+    process group inside the capture the first 2-GPU attempt did not complete within the box's time limit (round 2), so
+    bench.py uses the graph at N = 1 only and issues eagerly at N > 1 unless ``--graph`` is given."""
 
     def __init__(self, model, feats, metas, lifter=None, group=None, warmup=2):
         self.model, self.feats, self.metas, self.group = model, feats, metas, group

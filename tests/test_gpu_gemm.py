@@ -34,6 +34,15 @@ def test_linear_3xtf32_matches_fp64(M, N, K, relu, res):
     scale = ref.abs().max().item()
     print('3xTF32 GEMM M=%d N=%d K=%d: max abs err %.3e (cuBLAS fp32 %.3e), |y|max %.2f' % (M, N, K, err, err_cublas, scale))
     assert err < 2e-5 * max(scale, 1.0)
+    # the two pipelines (A operand in tensor memory -- default -- vs both operands in shared memory) compute the same products
+    # in the same order: identical results
+    from selfocc_b200 import _lib
+    _lib.load().so_linear_force_ss(1)
+    try:
+        y_ss = ops.linear_3xtf32(x, hi, lo, b, relu=relu, residual=r)
+    finally:
+        _lib.load().so_linear_force_ss(0)
+    assert torch.equal(y_ss, y)
 
 
 @pytest.mark.parametrize('rows,C,with_add', [(1000, 96, False), (81983, 96, True), (77, 128, False), (5, 200, True)])

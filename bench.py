@@ -245,6 +245,39 @@ def run_b200(args):
     total_ms, launches, clocks = timed(lambda: gather(step(feats_d, metas_d)), K, W, sampler, sample_clocks=True,
                                        finalize=gather_join if world > 1 else None)
     prof = _lib.profile_read()
+    ms_per_step_eager = total_ms / K
+    # The same step replayed from a CUDA graph (one capture per rank: ~95 launches of lift + decode + pack + render; the NCCL
+    # gather stays OUTSIDE the graph and reads a fresh packed copy of the outputs).  The eager pass above supplies the per-kernel
+    # breakdown (library events cannot be read back from a captured stream) and stays the fallback.
+    issue = 'eager issue'
+    if not args.no_graph:
+        try:
+            _lib.profile_enable(False)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(feats_d, metas_d)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_out = step(feats_d, metas_d)
+            ok, why = 1, ''
+        except Exception as e:
+            ok, why = 0, repr(e)[:200]
+        if world > 1:
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            def step_graph():
+                graph.replay()
+                return gather(g_out)
+            total_ms, _, _ = timed(step_graph, K, W, finalize=gather_join if world > 1 else None)
+            issue = 'CUDA graph replay of the step (collective outside the graph)'
+        else:
+            issue = 'eager issue (graph capture failed: %s)' % why
     ms_per_step = total_ms / K
     value = world * rays_per_frame / (ms_per_step * 1e-3)
 
@@ -372,7 +405,7 @@ def run_b200(args):
                        'color_dims': args.color_dims, 'render_bkgd': 'random' if has_rgb else 'white',
                        'outputs': 'depth, max_depth, acc, normal' + (', rgb' if has_rgb else ''),
                        'frames_per_step': world, 'parallelism': 'dp%d frames + 1 all_gather (async, overlaps the next lift)' % world,
-                       'l2_flush_between_steps': True},
+                       'l2_flush_between_steps': True, 'issue': issue, 'ms_per_step_eager': ms_per_step_eager},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'kernel_ms_per_step': breakdown}
     if strong is not None:

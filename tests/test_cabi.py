@@ -83,6 +83,38 @@ def test_entry_points_reject_bad_arguments_without_a_gpu():
                                        C.c_void_p(20), N) == -1
     assert lib.so_error_string(-2) == b'unsupported configuration'
     assert lib.so_render_workspace_floats(0) == 2 and lib.so_render_workspace_floats(24) == 48
+    # ---- round-2 entry points
+    assert lib.so_render_pack_floats(None) == 0 and lib.so_render_pack_floats(C.byref(big)) == 0
+    assert lib.so_render_pack_floats(C.byref(ok)) == 2 * 257 * 257 * 32            # n_feat 0: float2 z-pairs
+    ok3 = _lib.VolumeDesc()
+    ok3.H, ok3.W, ok3.Z, ok3.zpitch, ok3.n_feat, ok3.feat_pitch = 257, 257, 31, 32, 3, 4
+    for i in range(3):
+        ok3.axis[i].range0, ok3.axis[i].size0 = 51.2, 128.0
+    assert lib.so_render_pack_floats(C.byref(ok3)) == 4 * 257 * 257 * 31           # n_feat 3: float4 (r, g, b, sdf)
+    ok8 = _lib.VolumeDesc()
+    ok8.H, ok8.W, ok8.Z, ok8.zpitch, ok8.n_feat, ok8.feat_pitch = 9, 9, 5, 8, 8, 8
+    for i in range(3):
+        ok8.axis[i].range0, ok8.axis[i].size0 = 1.0, 4.0
+    assert lib.so_render_pack_floats(C.byref(ok8)) == 0                            # no packed form for 8 channels
+    assert lib.so_render_pack(one, N, C.byref(ok8), one, N) == -2
+    assert lib.so_render_pack(N, N, C.byref(ok), one, N) == -1
+    assert lib.so_render_pack(one, N, C.byref(ok3), one, N) == -1                  # colour pack without a feature volume
+    assert lib.so_render_infer_packed(N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N, N) == -1
+    assert lib.so_tpv_decode_rows(one, one, one, 96, one, one, one, one, C.byref(ok), 250, 10, one, N, N) == -1   # rows beyond H
+    assert lib.so_tpv_decode_rows(one, one, one, 96, one, one, one, one, C.byref(ok), 7, 0, one, N, N) == 0       # empty slab
+    assert lib.so_field_second_grad(N, C.byref(ok), one, 1, one, N) == -1
+    assert lib.so_field_second_grad(one, C.byref(ok), one, 0, one, N) == 0
+    assert lib.so_field_second_grad_backward(C.byref(ok), one, 1, N, one, N) == -1
+    assert lib.so_depth_metric_sample(N, one, 1, 1, 1, 1, one, N) == -1
+    assert lib.so_depth_metric_sample(one, one, 6, 0, 45, 80, one, N) == 0          # no LiDAR points: nothing to do
+    assert lib.so_depth_metric_sums(one, one, N, N, 6, 10, one, N) == -1
+    assert lib.so_flatten_level(one, one, one, one, 6, 96, 100, 50, 120, N) == -1   # level does not fit the token tensor
+    assert lib.so_flatten_level(N, one, one, one, 6, 96, 100, 0, 100, N) == -1
+    # strided attention entry points: odd offset pitch / mis-aligned offsets are refused (float2 loads)
+    assert lib.so_tpv_self_attn_forward_strided(one, one, one, one, one, one, one, 10, 6, 16, 4, 3, 4, 96, 6 * 3 * 4 * 2 + 1, 6 * 3 * 4, N) == -1
+    assert lib.so_tpv_self_attn_forward_strided(one, one, one, C.c_void_p(20), one, one, one, 10, 6, 16, 4, 3, 4, 96, 6 * 3 * 4 * 2, 6 * 3 * 4, N) == -1
+    for hook in (lib.so_attn_force_v1, lib.so_linear_force_ss, lib.so_render_train_force_sem_generic):
+        assert hook(1) == 0 and hook(0) == 0
 
 
 def test_product_never_imports_the_oracle_or_reads_the_reference():

@@ -268,6 +268,14 @@ int so_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, void* str
 int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                      float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 
+/* A9  projection + LayerNorm in ONE launch: y = LayerNorm(act(x w^T + bias) + residual) * gamma + beta over the N output
+ * columns, computed in the GEMM epilogue (an epilogue thread owns a whole output row, so the statistics are register-local).
+ * Replaces `output_proj -> (+ identity) -> norm` and `ffn.layers[1] -> (+ identity) -> norm` of TPVFormerLayer
+ * (tpvformer_encoder_layer.py:185-218).  N % 32 == 0, N <= 128; otherwise as so_linear_3xtf32. */
+int so_linear_3xtf32_ln(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                        const float* gamma, const float* beta, float eps, float* y, int64_t M, int32_t N, int32_t K,
+                        int32_t relu, void* stream);
+
 /* A9  y = LayerNorm(x [+ add]) over the last dimension C (nn.LayerNorm(C), biased variance, eps inside the sqrt),
  * replaces the norm steps of TPVFormerLayer (tpvformer_encoder_layer.py:185-196).  x, add, y [rows, C]; C <= 256. */
 int so_layer_norm(const float* x, const float* add, const float* gamma, const float* beta, float* y, int64_t rows,

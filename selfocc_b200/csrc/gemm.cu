@@ -91,11 +91,11 @@ static PipeCfg make_pipe_cfg_ts(int N, int K) {
   c.KA = K / kAtomK;
   c.w_bytes = 2 * c.KA * c.BN * 128;
   c.epi_bufs = 2;
-  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 4 + 256;
+  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 12 + 256;
   int budget = 227 * 1024 - 1024 - fixed;
   if (budget / kAtomBytesA < 3) {
     c.epi_bufs = 1;
-    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
+    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 12 + 256;
     budget = 227 * 1024 - 1024 - fixed;
   }
   c.stages = budget / kAtomBytesA;
@@ -110,11 +110,11 @@ static PipeCfg make_pipe_cfg(int N, int K) {
   c.KA = K / kAtomK;
   c.w_bytes = 2 * c.KA * c.BN * 128;
   c.epi_bufs = 2;
-  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 4 + 256;
+  int fixed = c.w_bytes + 4 * c.epi_bufs * kEpiWarpBytes + kMaxBN * 12 + 256;
   int budget = 227 * 1024 - 1024 - fixed;
   if (budget / kStageBytes < 3) {            // K = 192: the resident W tile leaves no room; keep the deeper load ring
     c.epi_bufs = 1;
-    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 4 + 256;
+    fixed = c.w_bytes + 4 * kEpiWarpBytes + kMaxBN * 12 + 256;
     budget = 227 * 1024 - 1024 - fixed;
   }
   c.stages = budget / kStageBytes;
@@ -306,6 +306,70 @@ linear_3xtf32_pipe_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
+// LayerNorm-fused epilogue of one 32-row slice of an m-tile (one epilogue warp, thread = row).  NCH = BN / 32 accumulator
+// chunks are read into registers (compile-time count: no local memory), the accumulator is released to the MMA warp right
+// away, then mean / variance (two passes over the registers), scale / shift, swizzled staging and one TMA store per chunk.
+template <int NCH>
+__device__ __forceinline__ void epilogue_ln(uint32_t tm, const float* __restrict__ bias_s, const float* __restrict__ gamma_s,
+                                            const float* __restrict__ beta_s, const float* __restrict__ residual, int relu, long long gr,
+                                            long long M, int N, float eps, uint8_t* tile0, int& ebuf, int epi_bufs, int lane,
+                                            const CUtensorMap* map_y, int row0, uint64_t* tmem_empty_bar) {
+  float v[NCH][32];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tm + (uint32_t)(c * 32), r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float t = __uint_as_float(r[i]) + bias_s[c * 32 + i];
+      if (relu) t = fmaxf(t, 0.f);
+      v[c][i] = t;
+    }
+    if (residual && gr < M) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + gr * N + c * 32 + 4 * j));
+        v[c][4 * j] += rr.x; v[c][4 * j + 1] += rr.y; v[c][4 * j + 2] += rr.z; v[c][4 * j + 3] += rr.w;
+      }
+    }
+  }
+  tc_fence_before();
+  mbar_arrive(tmem_empty_bar);                            // the accumulator is in registers: the MMA warp may overwrite it
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += v[c][i];
+  const float mean = sum / (float)(NCH * 32);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float d = v[c][i] - mean; sq = fmaf(d, d, sq); }
+  const float rstd = rsqrtf(sq / (float)(NCH * 32) + eps);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint8_t* tile = tile0 + ebuf * kEpiWarpBytes;
+    if (lane == 0) {
+      if (epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read();
+    }
+    if (epi_bufs == 2) ebuf ^= 1;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 o;
+      o.x = (v[c][4 * j] - mean) * rstd * gamma_s[c * 32 + 4 * j] + beta_s[c * 32 + 4 * j];
+      o.y = (v[c][4 * j + 1] - mean) * rstd * gamma_s[c * 32 + 4 * j + 1] + beta_s[c * 32 + 4 * j + 1];
+      o.z = (v[c][4 * j + 2] - mean) * rstd * gamma_s[c * 32 + 4 * j + 2] + beta_s[c * 32 + 4 * j + 2];
+      o.w = (v[c][4 * j + 3] - mean) * rstd * gamma_s[c * 32 + 4 * j + 3] + beta_s[c * 32 + 4 * j + 3];
+      *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) tma_store_2d(map_y, tile, c * 32, row0);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // TS variant of the pipeline: the A operand (X split into hi / lo) lives in TENSOR MEMORY instead of shared memory.
 // Why: with both operands in shared memory every one of the 12 MMAs of an atom re-reads a 4 KB A slice and a 4 KB B slice,
@@ -317,7 +381,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 linear_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                           const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_y,
                           const float* __restrict__ bias, const float* __restrict__ residual, long long M, int N, int BN, int KA,
-                          int stages, int n_tiles, int m_tiles, int relu, int epi_bufs) {
+                          int stages, int n_tiles, int m_tiles, int relu, int epi_bufs, const float* __restrict__ ln_gamma,
+                          const float* __restrict__ ln_beta, float ln_eps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_bytes = 2 * KA * BN * 128;
@@ -326,7 +391,9 @@ linear_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   uint8_t* ring = sm + w_bytes;                                   // stages x raw X atom (16 KB), 1 KB aligned
   uint8_t* epi = ring + stages * kAtomBytesA;                     // 4 x epi_bufs x 4 KB, 1 KB aligned (swizzle atoms)
   float* bias_s = reinterpret_cast<float*>(epi + 4 * epi_bufs * kEpiWarpBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kMaxBN);
+  float* gamma_s = bias_s + kMaxBN;                               // LayerNorm-fused epilogue (ln_gamma != nullptr): scale / shift
+  float* beta_s = gamma_s + kMaxBN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(beta_s + kMaxBN);
   uint64_t* w_full = bars;
   uint64_t* full = bars + 1;
   uint64_t* conv = full + kMaxStages;
@@ -449,13 +516,30 @@ linear_3xtf32_ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const int q = warp & 3;                              // TMEM lane quarter of this warp
     uint8_t* tile0 = epi + q * epi_bufs * kEpiWarpBytes;
     int ebuf = 0;
-    for (int i = tid - 256; i < BN; i += 128) bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+    for (int i = tid - 256; i < BN; i += 128) {
+      bias_s[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+      gamma_s[i] = (ln_gamma && n0 + i < N) ? __ldg(ln_gamma + n0 + i) : 0.f;
+      beta_s[i] = (ln_beta && n0 + i < N) ? __ldg(ln_beta + n0 + i) : 0.f;
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
     int acc = 0; uint32_t acc_ph = 0;
     for (int mt = group; mt < m_tiles; mt += n_groups) {
       mbar_wait(tmem_full + acc, acc_ph);
       tc_fence_after();
       const long long gr = (long long)mt * kBM + q * 32 + lane;      // this thread's output row
+      if (ln_gamma) {
+        // LayerNorm over the row (the launcher guarantees one n-tile: BN == N): y = LN(x W^T + b [relu] [+ residual]) * gamma + beta.
+        // A thread owns a whole output row, so the statistics need no cross-thread traffic.
+        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+        switch (BN >> 5) {
+          case 1: epilogue_ln<1>(tm, bias_s, gamma_s, beta_s, residual, relu, gr, M, N, ln_eps, tile0, ebuf, epi_bufs, lane, &map_y, mt * kBM + q * 32, tmem_empty + acc); break;
+          case 2: epilogue_ln<2>(tm, bias_s, gamma_s, beta_s, residual, relu, gr, M, N, ln_eps, tile0, ebuf, epi_bufs, lane, &map_y, mt * kBM + q * 32, tmem_empty + acc); break;
+          case 3: epilogue_ln<3>(tm, bias_s, gamma_s, beta_s, residual, relu, gr, M, N, ln_eps, tile0, ebuf, epi_bufs, lane, &map_y, mt * kBM + q * 32, tmem_empty + acc); break;
+          default: epilogue_ln<4>(tm, bias_s, gamma_s, beta_s, residual, relu, gr, M, N, ln_eps, tile0, ebuf, epi_bufs, lane, &map_y, mt * kBM + q * 32, tmem_empty + acc); break;
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        continue;
+      }
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + c0), r);
@@ -654,8 +738,28 @@ extern "C" int so_split_tf32(const float* w, float* hi, float* lo, int64_t n, vo
   return check_launch();
 }
 
+static int linear_impl(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual, float* y,
+                       int64_t M, int32_t N, int32_t K, int32_t relu, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                       void* stream);
+
 extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
                                 float* y, int64_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
+  return linear_impl(x, w_hi, w_lo, bias, residual, y, M, N, K, relu, nullptr, nullptr, 0.f, stream);
+}
+
+// y = LayerNorm(act(x w^T + bias) + residual) * gamma + beta over the N output columns, in the GEMM epilogue.
+// N must be a multiple of 32 and <= 128 (one n-tile holds the whole row); tensor-memory (TS) pipeline only.
+extern "C" int so_linear_3xtf32_ln(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual,
+                                   const float* gamma, const float* beta, float eps, float* y, int64_t M, int32_t N, int32_t K,
+                                   int32_t relu, void* stream) {
+  if (!gamma || !beta) return SO_ERR_INVALID_ARG;
+  if (N % 32 != 0 || N > 128 || g_linear_force_ss) return SO_ERR_UNSUPPORTED;
+  return linear_impl(x, w_hi, w_lo, bias, residual, y, M, N, K, relu, gamma, beta, eps, stream);
+}
+
+static int linear_impl(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* residual, float* y,
+                       int64_t M, int32_t N, int32_t K, int32_t relu, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                       void* stream) {
   if (!x || !w_hi || !w_lo || !y || M < 0 || N < 1 || K < 1) return SO_ERR_INVALID_ARG;
   if (K % (kChunkAtoms * kAtomK) != 0 || K > 192) return SO_ERR_UNSUPPORTED;      // K = 96 or 192
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15)
@@ -688,7 +792,8 @@ extern "C" int so_linear_3xtf32(const float* x, const float* w_hi, const float* 
   ProfScope prof(8, st);
   if (ts)
     linear_3xtf32_ts_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
-                                                                            cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs);
+                                                                            cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs,
+                                                                            ln_gamma, ln_beta, ln_eps);
   else
     linear_3xtf32_pipe_kernel<<<n_tiles * groups, kPipeThreads, cfg.smem, st>>>(mx, mhi, mlo, my, bias, residual, (long long)M, N, cfg.BN,
                                                                               cfg.KA, cfg.stages, n_tiles, m_tiles, relu, cfg.epi_bufs);

@@ -190,8 +190,7 @@ class ShardedLifter:
         ref = self._local_rows(st['ref'], rank, world).contiguous()
         out = ops_.tpv_self_attn_forward_rows(v, Hd, v.shape[1] // Hd, self.enc.tpv_spatial_shapes, self.enc.tpv_level_start,
                                               offs, logits, ref, L, P)
-        q = E.fast_linear(sa.output_proj, out, residual=q)
-        q = ops_.layer_norm(q, layer.norms[0].weight.detach(), layer.norms[0].bias.detach(), layer.norms[0].eps)
+        q = E.fast_linear(sa.output_proj, out, residual=q, ln=layer.norms[0])
         # -- image cross attention, one plane at a time (tpvformer/attention/image_cross_attention.py:83-93)
         feat = st['feat']
         n_cam, nv = feat.shape[0], feat.shape[1]
@@ -209,14 +208,12 @@ class ShardedLifter:
             vis = st['vises'][i][:, b:b + c].contiguous()
             slots = ops_.tpv_cross_attn_forward_rows(vrows[i], n_cam, da.num_heads, qi.shape[1] // da.num_heads, st['shapes'], st['lsi'],
                                                      offs, logits, uv, vis, da.num_levels, da.num_points)
-            outs.append(E.fast_linear(att.output_proj, slots, residual=qi))
+            outs.append(E.fast_linear(att.output_proj, slots, residual=qi, ln=layer.norms[1]))
             o0 += c
         q = torch.cat(outs, 0)
-        q = ops_.layer_norm(q, layer.norms[1].weight.detach(), layer.norms[1].bias.detach(), layer.norms[1].eps)
         ffn = layer.ffns[0]
         h = E.fast_linear(ffn.layers[0][0], q, relu=True)
-        q = E.fast_linear(ffn.layers[1], h, residual=q if ffn.add_identity else None)
-        return ops_.layer_norm(q, layer.norms[2].weight.detach(), layer.norms[2].bias.detach(), layer.norms[2].eps)
+        return E.fast_linear(ffn.layers[1], h, residual=q if ffn.add_identity else None, ln=layer.norms[2])
 
     # ---- exchange
     def pad_local(self, local, rank, world):

@@ -137,9 +137,33 @@ class _DeformBase(nn.Module):
         nn.init.constant_(self.value_proj.bias, 0.)
 
 
-def fast_linear(lin, x, relu=False, residual=None, out=None):
+def fast_linear(lin, x, relu=False, residual=None, out=None, ln=None):
     """nn.Linear forward for the inference path: the tcgen05 split-precision GEMM (``so_linear_3xtf32``) when the shape
-    allows it (K % 96 == 0), cuBLAS otherwise.  Split weights are cached per parameter version."""
+    allows it (K % 96 == 0), cuBLAS otherwise.  Split weights are cached per parameter version.
+    ``ln``: an nn.LayerNorm applied to the result; folded into the GEMM epilogue when the row fits one tile
+    (``so_linear_3xtf32_ln``), a separate ``so_layer_norm`` launch otherwise."""
+    if ln is not None:
+        N, K = lin.weight.shape
+        if x.is_cuda and x.dtype == torch.float32 and ops.linear_ln_supported(N, K) and not _ln_fusion_off():
+            return _fast_linear_impl(lin, x, relu, residual, out, (ln.weight.detach(), ln.bias.detach(), ln.eps))
+        y = _fast_linear_impl(lin, x, relu, residual, None, None)
+        if y.is_cuda and y.dtype == torch.float32 and y.shape[-1] <= 256:
+            y = ops.layer_norm(y.contiguous(), ln.weight.detach(), ln.bias.detach(), ln.eps)
+        else:
+            y = ln(y)
+        if out is not None:
+            out.copy_(y.view_as(out))
+            return out
+        return y
+    return _fast_linear_impl(lin, x, relu, residual, out, None)
+
+
+def _ln_fusion_off():
+    import os
+    return os.environ.get('SELFOCC_B200_NO_LN_FUSION', '0') == '1'          # A/B switch for measurements
+
+
+def _fast_linear_impl(lin, x, relu, residual, out, ln):
     w = lin.weight
     if x.is_cuda and x.dtype == torch.float32 and ops.linear_supported(w.shape[1], w.shape[0]):
         ver = (w._version, w.data_ptr())
@@ -149,7 +173,8 @@ def fast_linear(lin, x, relu=False, residual=None, out=None):
                 ent = (ver,) + ops.split_tf32(w.detach().contiguous())
             lin._so_split = ent
         return ops.linear_3xtf32(x.contiguous(), ent[1], ent[2], lin.bias.detach() if lin.bias is not None else None,
-                                 relu=relu, residual=None if residual is None else residual.contiguous(), out=out)
+                                 relu=relu, residual=None if residual is None else residual.contiguous(), out=out, ln=ln)
+    assert ln is None
     y = F.linear(x, w, lin.bias)
     if relu:
         y = F.relu(y)
@@ -208,7 +233,10 @@ class CrossViewHybridAttention(_DeformBase):
         nn.init.constant_(self.output_proj.bias, 0.)
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
-                reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+                reference_points=None, spatial_shapes=None, level_start_index=None, fuse_norm=None, **kwargs):
+        """fuse_norm: the nn.LayerNorm that follows this op in the layer (inference path only): applied inside the
+        output_proj GEMM's epilogue; the caller then skips its norm step (``self.fused_norm_applied``)."""
+        self.fused_norm_applied = False
         if value is None:
             value = query
         if identity is None:
@@ -239,7 +267,8 @@ class CrossViewHybridAttention(_DeformBase):
             if self.training:
                 out = self.dropout(fast_linear(self.output_proj, out)) + idt
             else:
-                out = fast_linear(self.output_proj, out, residual=idt)
+                out = fast_linear(self.output_proj, out, residual=idt, ln=fuse_norm)
+                self.fused_norm_applied = fuse_norm is not None
             return out[None] if self.batch_first else out[:, None]
         value = self.value_proj(value)
         if key_padding_mask is not None:
@@ -319,7 +348,7 @@ class BEVCrossAttention(nn.Module):
         nn.init.constant_(self.output_proj.bias, 0.)
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None,
-                bev_masks=None, level_start_index=None, bev_vis=None, value_rows=None, out_rows=None, **kwargs):
+                bev_masks=None, level_start_index=None, bev_vis=None, value_rows=None, out_rows=None, fuse_norm=None, **kwargs):
         """query [B,Q,C]; key/value [N, sum(hw), B, C]; reference_points_cams [N,B,Q,D,2];
         bev_masks [N,B,Q,D] (bool/uint8); bev_vis optional uint8 [N,Q] = any_D(mask) from so_point_sampling;
         value_rows optional [N*sum(hw), >= C] view holding value_proj(value) already (TPVCrossAttention projects the image
@@ -350,9 +379,12 @@ class BEVCrossAttention(nn.Module):
                 logits = fast_linear(da.attention_weights, query[0]).view(num_query, Hd, L, D)
                 slots = ops.tpv_cross_attn_forward(v_rows.contiguous().view(n_cam, nv, Hd, -1), spatial_shapes, level_start_index,
                                                    offsets, logits, uv, bev_vis.contiguous())
+            self.fused_norm_applied = False
             if self.training:
                 return self.dropout(fast_linear(self.output_proj, slots))[None] + residual
-            return fast_linear(self.output_proj, slots, residual=residual[0], out=out_rows)[None]
+            self.fused_norm_applied = fuse_norm is not None
+            return fast_linear(self.output_proj, slots, residual=residual[0], out=out_rows, ln=fuse_norm)[None]
+        self.fused_norm_applied = False
         slots = self._rebatch_forward(query, value, spatial_shapes, reference_points_cams, bev_masks, level_start_index)
         slots = self.output_proj(slots)
         return self.dropout(slots) + residual
@@ -401,7 +433,7 @@ class TPVCrossAttention(nn.Module):
         self.attns = [self.attn_hw, self.attn_zh, self.attn_wz]
 
     def forward(self, query, key, value, residual=None, spatial_shapes=None, reference_points_cams=None, tpv_masks=None,
-                level_start_index=None, tpv_vis=None, out_cat=None, **kwargs):
+                level_start_index=None, tpv_vis=None, out_cat=None, fuse_norm=None, **kwargs):
         rows = [None, None, None]
         vps = [a.deformable_attention.value_proj for a in self.attns]
         if value.shape[2] == 1 and _fusable(vps, value) and not _needs_grad(value, query[0], vps[0].weight):
@@ -414,11 +446,14 @@ class TPVCrossAttention(nn.Module):
                 n = query[i].shape[1]
                 outs[i] = out_cat[0, o0:o0 + n]
                 o0 += n
-        return [self.attns[i](query[i], key, value, residual[i] if residual is not None else None,
-                              spatial_shapes=spatial_shapes, level_start_index=level_start_index,
-                              reference_points_cams=reference_points_cams[i], bev_masks=tpv_masks[i],
-                              bev_vis=None if tpv_vis is None else tpv_vis[i], value_rows=rows[i], out_rows=outs[i])
-                for i in range(3)]
+        res = [self.attns[i](query[i], key, value, residual[i] if residual is not None else None,
+                             spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                             reference_points_cams=reference_points_cams[i], bev_masks=tpv_masks[i],
+                             bev_vis=None if tpv_vis is None else tpv_vis[i], value_rows=rows[i], out_rows=outs[i],
+                             fuse_norm=fuse_norm)
+               for i in range(3)]
+        self.fused_norm_applied = fuse_norm is not None and all(getattr(a, 'fused_norm_applied', False) for a in self.attns)
+        return res
 
 
 class FFN(nn.Module):
@@ -435,11 +470,13 @@ class FFN(nn.Module):
             nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(ffn_drop)),
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
 
-    def forward(self, x, identity=None):
+    def forward(self, x, identity=None, fuse_norm=None):
+        self.fused_norm_applied = False
         if not self.training and not _needs_grad(x, self.layers[0][0].weight):
             h = fast_linear(self.layers[0][0], x, relu=True)
             idt = (x if identity is None else identity) if self.add_identity else None
-            return fast_linear(self.layers[1], h, residual=idt)
+            self.fused_norm_applied = fuse_norm is not None
+            return fast_linear(self.layers[1], h, residual=idt, ln=fuse_norm)
         out = self.layers(x)
         if not self.add_identity:
             return out
@@ -523,16 +560,29 @@ class TPVFormerLayer(nn.Module):
         # avoids the reference's torch.cat before every self-attention / norm / ffn step (5 x 31 MB copies per layer).
         qc = _whole(query, split)
         cat = lambda views, whole: whole if whole is not None else torch.cat(views, dim=1)
-        for op in self.operation_order:
+        # inference: a 'norm' that directly follows an attention / ffn step is folded into that step's last GEMM
+        # (so_linear_3xtf32_ln); `skip_norm` marks it as done (the module reports whether it really applied it)
+        infer = query[0].is_cuda and query[0].dtype == torch.float32 and query[0].shape[0] == 1 and not self.training \
+            and not torch.is_grad_enabled()
+        order = list(self.operation_order)
+        skip_norm = False
+        for oi, op in enumerate(order):
+            nxt = self.norms[norm_i] if (infer and oi + 1 < len(order) and order[oi + 1] == 'norm' and not self.pre_norm) else None
             if op == 'self_attn':
                 q = cat(query, qc)
                 idt = (q if identity is query else torch.cat(identity, dim=1)) if self.pre_norm else None
-                qc = self.attentions[attn_i](q, q, q, idt, query_pos=pos_cat, reference_points=ref_2d,
-                                             spatial_shapes=tpv_levels[0], level_start_index=tpv_levels[1], **kwargs)
+                att = self.attentions[attn_i]
+                qc = att(q, q, q, idt, query_pos=pos_cat, reference_points=ref_2d,
+                         spatial_shapes=tpv_levels[0], level_start_index=tpv_levels[1], fuse_norm=nxt, **kwargs)
+                skip_norm = nxt is not None and getattr(att, 'fused_norm_applied', False)
                 query = torch.split(qc, split, 1)
                 attn_i += 1
                 identity = query
             elif op == 'norm':
+                if skip_norm:                       # already applied inside the previous step's GEMM epilogue
+                    skip_norm = False
+                    norm_i += 1
+                    continue
                 q = cat(query, qc)
                 ln = self.norms[norm_i]
                 if q.is_cuda and q.dtype == torch.float32 and q.shape[-1] <= 256 and not _needs_grad(q, ln.weight):
@@ -544,10 +594,12 @@ class TPVFormerLayer(nn.Module):
             elif op == 'cross_attn':
                 fused = query[0].is_cuda and not self.training and not _needs_grad(query[0], key)
                 buf = query[0].new_empty(1, sum(split), query[0].shape[-1]) if (fused and query[0].shape[0] == 1) else None
-                outs = self.attentions[attn_i](query, key, value, identity if self.pre_norm else None,
-                                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
-                                               reference_points_cams=reference_points_cams, tpv_masks=tpv_masks,
-                                               tpv_vis=tpv_vis, out_cat=buf, **kwargs)
+                att = self.attentions[attn_i]
+                outs = att(query, key, value, identity if self.pre_norm else None,
+                           spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                           reference_points_cams=reference_points_cams, tpv_masks=tpv_masks,
+                           tpv_vis=tpv_vis, out_cat=buf, fuse_norm=nxt if fused else None, **kwargs)
+                skip_norm = nxt is not None and fused and getattr(att, 'fused_norm_applied', False)
                 if buf is not None and all(o.data_ptr() == v.data_ptr() for o, v in zip(outs, torch.split(buf, split, 1))):
                     qc, query = buf, torch.split(buf, split, 1)       # the three planes were written in place
                 else:
@@ -557,7 +609,9 @@ class TPVFormerLayer(nn.Module):
             elif op == 'ffn':
                 q = cat(query, qc)
                 idt = (q if identity is query else torch.cat(identity, dim=1)) if self.pre_norm else None
-                qc = self.ffns[ffn_i](q, idt)
+                ffn = self.ffns[ffn_i]
+                qc = ffn(q, idt, fuse_norm=nxt)
+                skip_norm = nxt is not None and getattr(ffn, 'fused_norm_applied', False)
                 query = torch.split(qc, split, 1)
                 ffn_i += 1
         return query

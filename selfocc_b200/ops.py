@@ -433,9 +433,15 @@ def split_tf32(w):
     return hi, lo
 
 
-def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None, out=None):
+def linear_ln_supported(N, K):
+    """so_linear_3xtf32_ln: the whole output row must sit in one n-tile."""
+    return K in (96, 192) and N % 32 == 0 and N <= 128
+
+
+def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None, out=None, ln=None):
     """y = act(x @ w^T + bias) (+ residual) on tcgen05 tensor cores with fp32-level accuracy.  x [..., K] contiguous.
-    ``out``: optional pre-allocated contiguous [..., N] destination (e.g. a row range of a larger token buffer)."""
+    ``out``: optional pre-allocated contiguous [..., N] destination (e.g. a row range of a larger token buffer).
+    ``ln`` = (gamma, beta, eps): LayerNorm over the N outputs folded into the epilogue (so_linear_3xtf32_ln)."""
     lib = _lib.load()
     _chk(x, name='x'); _chk(w_hi, name='w_hi'); _chk(w_lo, name='w_lo'); _chk(bias, name='bias'); _chk(residual, name='residual')
     N, K = w_hi.shape
@@ -448,6 +454,12 @@ def linear_3xtf32(x, w_hi, w_lo, bias=None, relu=False, residual=None, out=None)
         assert y.numel() == M * N and y.shape[-1] == N
     if residual is not None:
         assert residual.numel() == y.numel()
+    if ln is not None:
+        gamma, beta, eps = ln
+        _chk(gamma, name='ln weight'); _chk(beta, name='ln bias')
+        _lib.check(lib.so_linear_3xtf32_ln(_p(x), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(gamma), _p(beta), float(eps), _p(y),
+                                           M, N, K, int(bool(relu)), _stream()), 'so_linear_3xtf32_ln')
+        return y
     _lib.check(lib.so_linear_3xtf32(_p(x), _p(w_hi), _p(w_lo), _p(bias), _p(residual), _p(y), M, N, K, int(bool(relu)), _stream()),
                'so_linear_3xtf32')
     return y

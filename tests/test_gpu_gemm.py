@@ -59,3 +59,33 @@ def test_layer_norm_matches_torch(rows, C, with_add):
     xin = x if a is None else x + a
     ref = torch.nn.functional.layer_norm(xin.double(), (C,), w.double(), b.double(), 1e-5)
     assert torch.allclose(y.double(), ref, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize('M,N,K,relu,res', [(1000, 96, 96, False, True), (5000, 96, 192, False, True), (300, 128, 96, True, False),
+                                            (77, 32, 96, False, False), (400, 64, 192, False, True), (81983, 96, 96, False, True)])
+def test_linear_with_layernorm_epilogue_matches_fp64(M, N, K, relu, res):
+    """so_linear_3xtf32_ln: y = LayerNorm(act(x w^T + b) + residual) * gamma + beta in the GEMM epilogue
+    (tpvformer_encoder_layer.py:185-218: output_proj / ffn -> + identity -> norm)."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    from selfocc_b200 import ops
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(M + 7 * N)
+    x = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.2).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    r = (3 * torch.randn(M, N, generator=g)).to(dev) if res else None
+    gamma, beta = (1 + 0.3 * torch.randn(N, generator=g)).to(dev), torch.randn(N, generator=g).to(dev)
+    hi, lo = ops.split_tf32(w)
+    y = ops.linear_3xtf32(x, hi, lo, b, relu=relu, residual=r, ln=(gamma, beta, 1e-5))
+    pre = x.double() @ w.double().t() + b.double()
+    if relu:
+        pre = pre.clamp(min=0)
+    if res:
+        pre = pre + r.double()
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma.double(), beta.double(), 1e-5)
+    err = (y.double() - ref).abs().max().item()
+    # and against the unfused sequence (GEMM kernel, then the LayerNorm kernel)
+    y2 = ops.layer_norm(ops.linear_3xtf32(x, hi, lo, b, relu=relu, residual=r), gamma, beta, 1e-5)
+    print('GEMM + LN epilogue M=%d N=%d K=%d: max abs err vs fp64 %.3e, vs unfused %.3e' % (M, N, K, err, (y - y2).abs().max().item()))
+    assert err < 3e-5 and torch.allclose(y, y2, atol=2e-5)

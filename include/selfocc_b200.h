@@ -90,6 +90,21 @@ int so_tpv_decode_rows(const float* tpv_hw, const float* tpv_zh, const float* tp
                        const float* b1, const float* w2, const float* b2, const so_volume_desc* vol_host, int32_t h_begin,
                        int32_t h_count, float* vol_sdf, float* vol_feat, void* stream);
 
+/* Backward of the decode MLP over one slab of h rows (training).  The two [rows x C x C] products of the slab run through
+ * so_linear_3xtf32; these are the element-wise pieces around them (reference: autograd through the decoder MLP,
+ * model/head/neus_head/bev_nerf.py:150-190).  rows = h_count * W * Z, voxel order (h, w, z) inside the slab.
+ *   features: a0[rows][C] = softplus(hw + zh + wz)
+ *   hidden:   z1_a1[rows][C] holds z1 = a0 W1^T + b1 on entry and a1 = softplus(z1) on return;
+ *             g1 = (W2^T g_out) * sigmoid(z1); g_out[rows][1 + n_feat] = the slab's output gradient gathered from
+ *             g_vol_sdf [H][W][zpitch] (may be NULL = zero) and g_vol_feat [H][W][Z][feat_pitch] (may be NULL = zero)
+ *   input:    g0[n] *= 1 - exp(-a0[n])   (= sigmoid of the pre-activation), n % 4 == 0                                   */
+int so_tpv_decode_bwd_features(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C,
+                               const so_volume_desc* vol_host, int32_t h_begin, int32_t h_count, float* a0, void* stream);
+int so_tpv_decode_bwd_hidden(float* z1_a1, const float* g_vol_sdf, const float* g_vol_feat, const float* w2, int32_t C,
+                             const so_volume_desc* vol_host, int32_t h_begin, int32_t h_count, float* g1, float* g_out,
+                             void* stream);
+int so_tpv_decode_bwd_input(float* g0, const float* a0, int64_t n, void* stream);
+
 /* Test hook: force the fp32 SIMT decode kernel (default: the tcgen05 3xTF32 kernel whenever C % 32 == 0). */
 int so_tpv_decode_force_simt(int on);
 

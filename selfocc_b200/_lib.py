@@ -49,6 +49,9 @@ SIGNATURES = {
     'so_profile_elapsed_ms': (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     'so_tpv_decode': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _P, _P, _P]),
     'so_tpv_decode_rows': (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, C.POINTER(VolumeDesc), _I, _I, _P, _P, _P]),
+    'so_tpv_decode_bwd_features': (C.c_int, [_P, _P, _P, _I, C.POINTER(VolumeDesc), _I, _I, _P, _P]),
+    'so_tpv_decode_bwd_hidden': (C.c_int, [_P, _P, _P, _P, _I, C.POINTER(VolumeDesc), _I, _I, _P, _P, _P]),
+    'so_tpv_decode_bwd_input': (C.c_int, [_P, _P, _L, _P]),
     'so_tpv_decode_force_simt': (C.c_int, [C.c_int]),
     'so_render_train_force_fwd32': (C.c_int, [C.c_int]),
     'so_render_train_force_sem_generic': (C.c_int, [C.c_int]),

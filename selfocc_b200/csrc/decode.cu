@@ -419,3 +419,128 @@ extern "C" int so_tpv_decode_rows(const float* tpv_hw, const float* tpv_zh, cons
     default: return SO_ERR_UNSUPPORTED;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of the decode MLP, one slab of h rows at a time (reference: autograd through TPVDecoder.forward,
+// model/head/base_head... the SDF/colour MLP in model/head/neus_head/bev_nerf.py:150-190 at the 1.65 M voxel centres).
+// The two M x C x C products of each slab run on the tcgen05 3xTF32 GEMM (so_linear_3xtf32); the kernels here are the
+// element-wise pieces fused around them so every slab intermediate is written once and read once:
+//   features:  a0 = softplus(hw + zh + wz)                                       (recomputed, never stored by forward)
+//   hidden:    z1 -> a1 = softplus(z1);  g1 = (W2^T g_out) * sigmoid(z1);  g_out packed [rows][n_out]
+//   input:     g0 *= sigmoid(f) = 1 - exp(-a0)
+// sigmoid(x) = 1 - exp(-softplus(x)) lets the activations be reused without keeping the pre-activations.
+__global__ void __launch_bounds__(256) decode_bwd_features_kernel(const float* __restrict__ hw, const float* __restrict__ zh,
+                                                                  const float* __restrict__ wz, int C4, int H, int W, int Z,
+                                                                  int h_begin, long long n_vec, float4* __restrict__ a0) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / C4;
+    int c4 = (int)(i - v * C4);
+    int z = (int)(v % Z);
+    long long t = v / Z;
+    int w = (int)(t % W), h = h_begin + (int)(t / W);
+    float4 a = __ldg(reinterpret_cast<const float4*>(hw + ((size_t)h * W + w) * C4 * 4) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(zh + ((size_t)z * H + h) * C4 * 4) + c4);
+    float4 c = __ldg(reinterpret_cast<const float4*>(wz + ((size_t)w * Z + z) * C4 * 4) + c4);
+    a0[i] = make_float4(softplus_fast(a.x + b.x + c.x), softplus_fast(a.y + b.y + c.y), softplus_fast(a.z + b.z + c.z),
+                        softplus_fast(a.w + b.w + c.w));
+  }
+}
+
+constexpr int kBwdMaxOut = 32;
+__global__ void __launch_bounds__(256) decode_bwd_hidden_kernel(float4* __restrict__ z1_a1, const float* __restrict__ g_vs,
+                                                                const float* __restrict__ g_vf, const float* __restrict__ w2,
+                                                                int C4, int W, int Z, int zpitch, int n_out, int feat_pitch,
+                                                                int h_begin, long long n_vec, float4* __restrict__ g1,
+                                                                float* __restrict__ g_out) {
+  extern __shared__ float4 w2s[];  // [n_out][C4]
+  for (int i = threadIdx.x; i < n_out * C4; i += blockDim.x) w2s[i] = __ldg(reinterpret_cast<const float4*>(w2) + i);
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / C4;
+    int c4 = (int)(i - v * C4);
+    int z = (int)(v % Z);
+    long long col = (long long)h_begin * W + v / Z;  // (h, w) column of the full volume
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float go = g_vs ? __ldg(g_vs + col * zpitch + z) : 0.f;
+    {
+      float4 wv = w2s[c4];
+      acc.x = go * wv.x; acc.y = go * wv.y; acc.z = go * wv.z; acc.w = go * wv.w;
+    }
+    if (c4 == 0) g_out[v * n_out] = go;
+    const float* gf = g_vf ? g_vf + (col * Z + z) * feat_pitch : nullptr;
+    for (int o = 1; o < n_out; ++o) {
+      float g = gf ? __ldg(gf + o - 1) : 0.f;
+      float4 wv = w2s[o * C4 + c4];
+      acc.x = fmaf(g, wv.x, acc.x); acc.y = fmaf(g, wv.y, acc.y); acc.z = fmaf(g, wv.z, acc.z); acc.w = fmaf(g, wv.w, acc.w);
+      if (c4 == 0) g_out[v * n_out + o] = g;
+    }
+    float4 zv = z1_a1[i];
+    float4 a = make_float4(softplus_fast(zv.x), softplus_fast(zv.y), softplus_fast(zv.z), softplus_fast(zv.w));
+    z1_a1[i] = a;
+    g1[i] = make_float4(acc.x * (1.f - __expf(-a.x)), acc.y * (1.f - __expf(-a.y)), acc.z * (1.f - __expf(-a.z)),
+                        acc.w * (1.f - __expf(-a.w)));
+  }
+}
+
+__global__ void __launch_bounds__(256) decode_bwd_input_kernel(float4* __restrict__ g0, const float4* __restrict__ a0, long long n_vec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = g0[i], a = __ldg(a0 + i);
+    g0[i] = make_float4(g.x * (1.f - __expf(-a.x)), g.y * (1.f - __expf(-a.y)), g.z * (1.f - __expf(-a.z)), g.w * (1.f - __expf(-a.w)));
+  }
+}
+
+static inline bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+static int bwd_slab_check(const so_volume_desc* d, int32_t C, int32_t h_begin, int32_t h_count) {
+  int rc = validate_volume(d);
+  if (rc) return rc;
+  if (C <= 0 || C % 4) return SO_ERR_UNSUPPORTED;
+  if (h_begin < 0 || h_count < 0 || h_begin + h_count > d->H) return SO_ERR_INVALID_ARG;
+  return SO_OK;
+}
+static unsigned bwd_grid(long long n_vec) {
+  long long g = ceil_div64(n_vec, 256), cap = (long long)kNumSMs * 16;
+  return (unsigned)(g < cap ? g : cap);
+}
+
+extern "C" int so_tpv_decode_bwd_features(const float* tpv_hw, const float* tpv_zh, const float* tpv_wz, int32_t C,
+                                          const so_volume_desc* d, int32_t h_begin, int32_t h_count, float* a0, void* stream) {
+  if (!tpv_hw || !tpv_zh || !tpv_wz || !a0) return SO_ERR_INVALID_ARG;
+  int rc = bwd_slab_check(d, C, h_begin, h_count);
+  if (rc) return rc;
+  if (misaligned16(tpv_hw) || misaligned16(tpv_zh) || misaligned16(tpv_wz) || misaligned16(a0)) return SO_ERR_INVALID_ARG;
+  long long n_vec = (long long)h_count * d->W * d->Z * (C / 4);
+  if (n_vec == 0) return SO_OK;
+  decode_bwd_features_kernel<<<bwd_grid(n_vec), 256, 0, (cudaStream_t)stream>>>(tpv_hw, tpv_zh, tpv_wz, C / 4, d->H, d->W, d->Z, h_begin,
+                                                                              n_vec, reinterpret_cast<float4*>(a0));
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_tpv_decode_bwd_hidden(float* z1_a1, const float* g_vol_sdf, const float* g_vol_feat, const float* w2, int32_t C,
+                                        const so_volume_desc* d, int32_t h_begin, int32_t h_count, float* g1, float* g_out,
+                                        void* stream) {
+  if (!z1_a1 || !w2 || !g1 || !g_out) return SO_ERR_INVALID_ARG;
+  int rc = bwd_slab_check(d, C, h_begin, h_count);
+  if (rc) return rc;
+  const int n_out = 1 + d->n_feat;
+  if (n_out > kBwdMaxOut) return SO_ERR_UNSUPPORTED;
+  if (misaligned16(z1_a1) || misaligned16(w2) || misaligned16(g1)) return SO_ERR_INVALID_ARG;
+  long long n_vec = (long long)h_count * d->W * d->Z * (C / 4);
+  if (n_vec == 0) return SO_OK;
+  size_t smem = (size_t)n_out * C * sizeof(float);
+  if (smem > 48 * 1024) return SO_ERR_UNSUPPORTED;
+  decode_bwd_hidden_kernel<<<bwd_grid(n_vec), 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(z1_a1), g_vol_sdf, d->n_feat ? g_vol_feat : nullptr, w2, C / 4, d->W, d->Z, d->zpitch, n_out, d->feat_pitch,
+      h_begin, n_vec, reinterpret_cast<float4*>(g1), g_out);
+  note_launch(1);
+  return check_launch();
+}
+
+extern "C" int so_tpv_decode_bwd_input(float* g0, const float* a0, int64_t n, void* stream) {
+  if (!g0 || !a0 || n < 0 || n % 4) return SO_ERR_INVALID_ARG;
+  if (misaligned16(g0) || misaligned16(a0)) return SO_ERR_INVALID_ARG;
+  if (n == 0) return SO_OK;
+  decode_bwd_input_kernel<<<bwd_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(g0), reinterpret_cast<const float4*>(a0), n / 4);
+  note_launch(1);
+  return check_launch();
+}

@@ -381,8 +381,13 @@ class FieldSecondGradFunction(torch.autograd.Function):
 
 
 class TPVDecodeFunction(torch.autograd.Function):
-    """Decode with the fused sm_100a forward.  Backward (training only) recomputes the MLP slab by slab with
-    torch/cuBLAS -- bounded memory, never the reference's 750 MB intermediate; a native backward kernel is future work."""
+    """Decode with the fused sm_100a forward.  Backward (training only) recomputes the MLP slab by slab -- bounded memory,
+    never the reference's 750 MB intermediate.  Default: the native slab backward (_backward_native: tcgen05 3xTF32 GEMMs
+    + the fused element-wise kernels so_tpv_decode_bwd_*); SELFOCC_B200_DECODE_BWD=torch or an unsupported channel count
+    takes the torch/cuBLAS autograd restatement of the same slab (_backward_torch), which is also what the tests compare
+    the native path with."""
+
+    SLAB_ROWS = 32
 
     @staticmethod
     def forward(ctx, hw, zh, wz, w1, b1, w2, b2, desc):
@@ -395,9 +400,57 @@ class TPVDecodeFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_vs, g_vf):
+        import os
+        saved, d = ctx.saved_tensors, ctx.desc
+        Cc = saved[0].shape[-1]
+        native = os.environ.get('SELFOCC_B200_DECODE_BWD', 'native') != 'torch' and linear_supported(Cc, Cc) \
+            and tuple(saved[3].shape) == (Cc, Cc) and 1 + d.n_feat <= 32
+        fn = TPVDecodeFunction._backward_native if native else TPVDecodeFunction._backward_torch
+        return (*fn(saved, d, g_vs, g_vf), None)
+
+    @staticmethod
+    def _backward_native(saved, d, g_vs, g_vf):
+        lib = _lib.load()
+        hw, zh, wz, w1, b1, w2, b2 = [t.contiguous() for t in saved]
+        H, W, Z, Cc, n_out = d.H, d.W, d.Z, hw.shape[-1], 1 + d.n_feat
+        dev = hw.device
+        g_vs = g_vs.contiguous() if g_vs is not None else None
+        g_vf = g_vf.contiguous() if (g_vf is not None and d.n_feat) else None
+        w1_hi, w1_lo = split_tf32(w1)
+        w1t_hi, w1t_lo = split_tf32(w1.t().contiguous())
+        g_hw, g_zh, g_wz = torch.empty_like(hw), torch.empty_like(zh), torch.zeros_like(wz)
+        g_w1, g_b1, g_w2, g_b2 = (torch.zeros_like(t) for t in (w1, b1, w2, b2))
+        step = min(H, TPVDecodeFunction.SLAB_ROWS)
+        rows_max = step * W * Z
+        a0b, z1b, g1b = (torch.empty(rows_max, Cc, device=dev) for _ in range(3))
+        gob = torch.empty(rows_max, n_out, device=dev)
+        st = _stream()
+        for h0 in range(0, H, step):
+            nh = min(H, h0 + step) - h0
+            rows = nh * W * Z
+            a0, z1, g1, go = a0b[:rows], z1b[:rows], g1b[:rows], gob[:rows]
+            _lib.check(lib.so_tpv_decode_bwd_features(_p(hw), _p(zh), _p(wz), Cc, C.byref(d), h0, nh, _p(a0), st),
+                       'so_tpv_decode_bwd_features')
+            linear_3xtf32(a0, w1_hi, w1_lo, b1, out=z1)
+            _lib.check(lib.so_tpv_decode_bwd_hidden(_p(z1), _p(g_vs), _p(g_vf), _p(w2), Cc, C.byref(d), h0, nh, _p(g1), _p(go), st),
+                       'so_tpv_decode_bwd_hidden')
+            # weight gradients: reductions over the slab's rows (cuBLAS; z1 now holds a1)
+            g_w2.addmm_(go.t(), z1)
+            g_b2.add_(go.sum(0))
+            g_w1.addmm_(g1.t(), a0)
+            g_b1.add_(g1.sum(0))
+            g0 = linear_3xtf32(g1, w1t_hi, w1t_lo, None, out=z1)          # a1 no longer needed
+            _lib.check(lib.so_tpv_decode_bwd_input(_p(g0), _p(a0), g0.numel(), st), 'so_tpv_decode_bwd_input')
+            g4 = g0.view(nh, W, Z, Cc)
+            g_hw.view(H, W, Cc)[h0:h0 + nh] = g4.sum(2)
+            g_zh.view(Z, H, Cc)[:, h0:h0 + nh] = g4.sum(1).permute(1, 0, 2)
+            g_wz.view(W, Z, Cc).add_(g4.sum(0))
+        return g_hw, g_zh, g_wz, g_w1, g_b1, g_w2, g_b2
+
+    @staticmethod
+    def _backward_torch(saved, d, g_vs, g_vf):
         import torch.nn.functional as F
-        hw, zh, wz, w1, b1, w2, b2 = ctx.saved_tensors
-        d = ctx.desc
+        hw, zh, wz, w1, b1, w2, b2 = saved
         H, W, Z, Cc = d.H, d.W, d.Z, hw.shape[-1]
         g_out = g_vs[..., :Z, None]
         if d.n_feat:
@@ -420,7 +473,7 @@ class TPVDecodeFunction(torch.autograd.Function):
             grads[2].view(W, Z, Cc).add_(gs[2])
             for i in range(4):
                 grads[3 + i] += gs[3 + i]
-        return (*grads, None)
+        return tuple(grads)
 
 
 # --------------------------------------------------------------------------------------- A6/A9 tensor-core projections

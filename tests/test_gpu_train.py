@@ -267,3 +267,48 @@ def test_head_forward_with_the_shipped_occ_config_options():
     loss = out['second_grad'].abs().mean() + out['ms_depths'][0].mean() + out['sem'][0].sum() * 1e-3
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in planes)
+
+
+@pytest.mark.parametrize('n_feat,hw,d,slab', [(0, 12, 6, 5), (3, 9, 5, 32), (24, 7, 4, 3)])
+def test_decode_backward_native_matches_oracle_autograd(n_feat, hw, d, slab, monkeypatch):
+    """TPVDecodeFunction.backward, native slab path (tcgen05 GEMMs + so_tpv_decode_bwd_*): gradients of every plane and
+    MLP parameter vs fp64 autograd through the oracle's decode (oracle/render.py:tpv_decode_ref), with several ragged slabs;
+    the torch/cuBLAS restatement of the same slab (SELFOCC_B200_DECODE_BWD=torch) must agree as well."""
+    dev = _dev()
+    from oracle import render as orender
+    from selfocc_b200 import ops
+    margs, _ = synth.small_mapping(hw, d)
+    m = GridMeterMapping(**margs)
+    H, W, Z, C = m.size_h, m.size_w, m.size_d, 96
+    planes = synth.random_planes(m, C, scale=1.0, seed=4)
+    mlp = synth.random_mlp(C, 1 + n_feat, seed=4)
+    desc = m.volume_desc(n_feat)
+    g = torch.Generator().manual_seed(9)
+    g_sdf = torch.randn(H, W, Z, generator=g)
+    g_feat = torch.randn(H, W, Z, max(n_feat, 1), generator=g)
+
+    ins64 = [t.double().requires_grad_(True) for t in (*planes, *mlp)]
+    ref = orender.tpv_decode_ref(*ins64[:3], (H, W, Z), *ins64[3:])            # [Cf, H, W, Z]
+    loss = (ref[0] * g_sdf.double()).sum()
+    if n_feat:
+        loss = loss + (ref[1:].permute(1, 2, 3, 0) * g_feat.double()).sum()
+    gref = torch.autograd.grad(loss, ins64)
+
+    def run(mode):
+        monkeypatch.setenv('SELFOCC_B200_DECODE_BWD', mode)
+        monkeypatch.setattr(ops.TPVDecodeFunction, 'SLAB_ROWS', slab)
+        ins = [t.to(dev).requires_grad_(True) for t in (*planes, *mlp)]
+        vs, vf = ops.TPVDecodeFunction.apply(*ins, desc)
+        l = (vs[..., :Z] * g_sdf.to(dev)).sum()
+        if n_feat:
+            l = l + (vf[..., :n_feat] * g_feat.to(dev)).sum()
+        return [t.cpu() for t in torch.autograd.grad(l, ins)]
+
+    names = ('tpv_hw', 'tpv_zh', 'tpv_wz', 'w1', 'b1', 'w2', 'b2')
+    for mode in ('native', 'torch'):
+        got = run(mode)
+        for n, a, b in zip(names, got, gref):
+            scale = b.abs().max().item() + 1e-12
+            err = (a.double() - b).abs().max().item() / scale
+            print('decode backward (%s) %s rel-to-max err %.2e' % (mode, n, err))
+            assert err < 2e-4, (mode, n, err)

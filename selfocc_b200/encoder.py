@@ -185,6 +185,21 @@ def _fast_linear_impl(lin, x, relu, residual, out, ln):
     return y
 
 
+def train_linear(lin, x):
+    """nn.Linear inside the autograd (training) path: forward and input gradient on the tcgen05 3xTF32 GEMM
+    (ops.TCLinearFunction) when the shape allows it; SELFOCC_B200_TRAIN_LINEAR=cublas keeps the stock nn.Linear."""
+    w = lin.weight
+    if x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.numel() > 0 \
+            and ops.linear_supported(w.shape[1], w.shape[0]) and _needs_grad(x, w) and not _train_linear_off():
+        return ops.TCLinearFunction.apply(x, w, lin.bias)
+    return lin(x)
+
+
+def _train_linear_off():
+    import os
+    return os.environ.get('SELFOCC_B200_TRAIN_LINEAR', 'tc') == 'cublas'
+
+
 def fast_linear_cat(owner, key, lins, x):
     """Several nn.Linear layers applied to the SAME input as one tcgen05 GEMM (weights concatenated along N, cached on
     ``owner``).  Returns the [M, sum(N_i)] result and the column slices (views, unit column stride) of each layer."""
@@ -270,17 +285,17 @@ class CrossViewHybridAttention(_DeformBase):
                 out = fast_linear(self.output_proj, out, residual=idt, ln=fuse_norm)
                 self.fused_norm_applied = fuse_norm is not None
             return out[None] if self.batch_first else out[:, None]
-        value = self.value_proj(value)
+        value = train_linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, Hd, -1)
-        offsets = self.sampling_offsets(query).view(bs, num_query, Hd, L, P, 2)
-        logits = self.attention_weights(query).view(bs, num_query, Hd, L * P)
+        offsets = train_linear(self.sampling_offsets, query).view(bs, num_query, Hd, L, P, 2)
+        logits = train_linear(self.attention_weights, query).view(bs, num_query, Hd, L * P)
         aw = logits.softmax(-1).view(bs, num_query, Hd, L, P)
         normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).to(offsets.dtype)
         loc = reference_points[:, :, None, :, :, :] + offsets / normalizer[None, None, None, :, None, :]
         out = ops.MultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index, loc, aw, self.im2col_step)
-        out = self.output_proj(out)
+        out = train_linear(self.output_proj, out)
         if not self.batch_first:
             out = out.permute(1, 0, 2)
         return self.dropout(out) + identity
@@ -312,12 +327,12 @@ class BEVDeformableAttention(_DeformBase):
         bs, num_query, _ = query.shape
         num_value = value.shape[1]
         Hd, L, P = self.num_heads, self.num_levels, self.num_points
-        value = self.value_proj(value)
+        value = train_linear(self.value_proj, value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, Hd, -1)
-        offsets = self.sampling_offsets(query).view(bs, num_query, Hd, L, P, 2)
-        aw = self.attention_weights(query).view(bs, num_query, Hd, L * P).softmax(-1).view(bs, num_query, Hd, L, P)
+        offsets = train_linear(self.sampling_offsets, query).view(bs, num_query, Hd, L, P, 2)
+        aw = train_linear(self.attention_weights, query).view(bs, num_query, Hd, L * P).softmax(-1).view(bs, num_query, Hd, L, P)
         if reference_points.shape[-1] != 2:
             raise ValueError('Last dim of reference_points must be 2, but get %d instead.' % reference_points.shape[-1])
         normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).to(offsets.dtype)
@@ -386,7 +401,7 @@ class BEVCrossAttention(nn.Module):
             return fast_linear(self.output_proj, slots, residual=residual[0], out=out_rows, ln=fuse_norm)[None]
         self.fused_norm_applied = False
         slots = self._rebatch_forward(query, value, spatial_shapes, reference_points_cams, bev_masks, level_start_index)
-        slots = self.output_proj(slots)
+        slots = train_linear(self.output_proj, slots)
         return self.dropout(slots) + residual
 
     def _rebatch_forward(self, query, value, spatial_shapes, ref_cams, masks, level_start_index):
@@ -477,7 +492,8 @@ class FFN(nn.Module):
             idt = (x if identity is None else identity) if self.add_identity else None
             self.fused_norm_applied = fuse_norm is not None
             return fast_linear(self.layers[1], h, residual=idt, ln=fuse_norm)
-        out = self.layers(x)
+        l0 = self.layers[0]
+        out = self.layers[2](train_linear(self.layers[1], l0[2](F.relu(train_linear(l0[0], x)))))
         if not self.add_identity:
             return out
         return (x if identity is None else identity) + out

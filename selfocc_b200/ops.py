@@ -524,6 +524,42 @@ def linear_supported(K, N=None):
     return K in (96, 192) and (N is None or N % 4 == 0)
 
 
+class TCLinearFunction(torch.autograd.Function):
+    """nn.Linear for the TRAINING path of the lifting encoder: y = x w^T + b and dL/dx = dL/dy w on the tcgen05 3xTF32 GEMM
+    (fp32-level accuracy, so the step stays an fp32 step: mmcv's Linear layers run cuBLAS fp32 SIMT kernels there); the
+    weight gradient is a reduction over the 10^5 token rows (dL/dy^T x, K = rows), which so_linear_3xtf32's tiling does not
+    cover, and stays on cuBLAS.  When the contraction of dL/dx (the layer's out_features) is not 96 / 192 it takes cuBLAS too."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        hi, lo = split_tf32(w.detach().contiguous())
+        y = linear_3xtf32(x2, hi, lo, None if b is None else b.detach().contiguous())
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias, ctx.xshape = b is not None, x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        N, K = w.shape
+        g2 = gy.reshape(-1, N).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if linear_supported(N, K):
+                hi, lo = split_tf32(w.detach().t().contiguous())
+                gx = linear_3xtf32(g2, hi, lo, None)
+            else:
+                gx = g2 @ w.detach()
+            gx = gx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
 def flatten_levels(img_feats, cams_embeds, level_embeds):
     """A3: [1, N, C, h, w] x L -> [N, sum(hw), 1, C] with camera + level embeddings, one transposing pass per level."""
     lib = _lib.load()

@@ -89,3 +89,28 @@ def test_linear_with_layernorm_epilogue_matches_fp64(M, N, K, relu, res):
     y2 = ops.layer_norm(ops.linear_3xtf32(x, hi, lo, b, relu=relu, residual=r), gamma, beta, 1e-5)
     print('GEMM + LN epilogue M=%d N=%d K=%d: max abs err vs fp64 %.3e, vs unfused %.3e' % (M, N, K, err, (y - y2).abs().max().item()))
     assert err < 3e-5 and torch.allclose(y, y2, atol=2e-5)
+
+
+@pytest.mark.parametrize('M,K,N,bias', [(1000, 96, 96, True), (777, 96, 192, True), (1300, 192, 96, False), (515, 96, 144, True)])
+def test_tc_linear_function_matches_fp64_autograd(M, K, N, bias):
+    """ops.TCLinearFunction (training-path nn.Linear): output, input gradient, weight and bias gradients vs fp64 F.linear.
+    N = 144: the input gradient's contraction is not 96 / 192 and takes the cuBLAS branch."""
+    import torch.nn.functional as F
+    if not torch.cuda.is_available():
+        pytest.skip('needs CUDA')
+    from selfocc_b200 import ops
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g)
+    w, b, gy = torch.randn(N, K, generator=g) * 0.2, torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ins64 = [t.double().requires_grad_(True) for t in ((x, w, b) if bias else (x, w))]
+    y64 = F.linear(*ins64)
+    g64 = torch.autograd.grad(y64, ins64, gy.double())
+    ins = [t.to(dev).requires_grad_(True) for t in ((x, w, b) if bias else (x, w))]
+    y = ops.TCLinearFunction.apply(ins[0], ins[1], ins[2] if bias else None)
+    got = torch.autograd.grad(y, ins, gy.to(dev))
+    assert (y.cpu().double() - y64).abs().max().item() < 2e-5 * y64.abs().max().item()
+    for name, a, r in zip(('x', 'w', 'b'), got, g64):
+        err = (a.cpu().double() - r).abs().max().item() / r.abs().max().item()
+        print('TCLinear grad %s rel-to-max err %.2e' % (name, err))
+        assert err < 2e-5, (name, err)

@@ -250,6 +250,7 @@ def run_b200(args):
     # gather stays OUTSIDE the graph and reads a fresh packed copy of the outputs).  The eager pass above supplies the per-kernel
     # breakdown (library events cannot be read back from a captured stream) and stays the fallback.
     issue = 'eager issue'
+    have_graph = False
     if not args.no_graph:
         try:
             _lib.profile_enable(False)
@@ -270,6 +271,7 @@ def run_b200(args):
             flag = torch.tensor([ok], device=dev, dtype=torch.int32)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = int(flag.item())
+        have_graph = bool(ok)
         if ok:
             def step_graph():
                 graph.replay()
@@ -332,42 +334,92 @@ def run_b200(args):
                 ((o['ms_colors'][0].reshape(-1, 3),) if has_rgb else ())
         hosts = [out_h[0], out_h[1]] + ([rgb_h] if has_rgb else [])
 
+        # the camera matrices of the step travel from PINNED host memory (non-blocking) into the device tensors the step reads:
+        # a pageable upload would synchronise the stream on every call and expose the host's launch time
+        l2i_h = torch.as_tensor(np.asarray(metas[0]['lidar2img']), dtype=torch.float32).pin_memory()
+        i2l_h = torch.as_tensor(np.asarray(metas[0]['img2lidar']), dtype=torch.float32).pin_memory()
+
+        def metas_upload():
+            metas_d[0]['lidar2img'].copy_(l2i_h, non_blocking=True)
+            metas_d[0]['img2lidar'].copy_(i2l_h, non_blocking=True)
+            return metas_d
+
+        def compute_eager(fd):
+            return step(fd, metas_upload())
+
+        def compute_graph(fd):
+            """the captured step (it reads feats_d / metas_d and writes g_out): stage this frame's uploaded inputs into the
+            graph's input tensors, replay, and hand out copies of the outputs so that the download of frame k does not
+            race with the replay of frame k+1 (two device-to-device copies, 58 + 173 MB: ~0.1 ms)"""
+            for d_, s_ in zip(feats_d, fd):
+                d_.copy_(s_, non_blocking=True)
+            metas_upload()
+            graph.replay()
+            keys = ('ms_depths', 'ms_max_depths') + (('ms_colors',) if has_rgb else ())
+            return {k: [g_out[k][0].clone()] for k in keys}
+        compute = compute_graph if have_graph else compute_eager
+        issue_e2e = 'CUDA graph replay' if have_graph else 'eager issue'
+
         def step_e2e():
             fd = [f.to(dev, non_blocking=True) for f in feats_h]     # H2D of this step's inputs (pinned)
-            out = step(fd, metas)                                    # numpy metas: matrices uploaded per call like the reference
+            out = compute(fd)
             for h, t in zip(hosts, fetch(out)):
                 h.copy_(t, non_blocking=True)
             return gather(out) if world > 1 else None
         _lib.profile_enable(False)
         # the same frames through selfocc_b200.pipeline.FramePipeline: upload of frame k+1 and download of frame k overlap
         # the compute of their neighbours (every step still uploads its inputs and downloads its result inside the region)
-        step_fn, finalize, mode = step_e2e, (gather_join if world > 1 else None), 'serial copies on the compute stream'
+        step_fn, finalize, mode = step_e2e, (gather_join if world > 1 else None), 'serial copies on the compute stream, ' + issue_e2e
         if not args.no_e2e_pipeline:
             try:
                 from selfocc_b200.pipeline import FramePipeline
-                pipe = FramePipeline(lambda fd: step(fd, metas), fetch, hosts, dev)
+                pipe = FramePipeline(compute, fetch, hosts, dev)
 
                 def step_pipe():
                     out = pipe.submit(feats_h, next_host=feats_h)
                     return gather(out) if world > 1 else None
-                pipe.submit(feats_h, next_host=feats_h)              # one probe frame outside the timed region (no collective)
+                probe = pipe.submit(feats_h, next_host=feats_h)      # one probe frame outside the timed region (no collective)
                 pipe.drain()
                 torch.cuda.synchronize()
+                if not torch.equal(out_h[0], probe['ms_depths'][0].reshape(-1).cpu()):
+                    raise RuntimeError('downloaded depth differs from the device result')
                 ok, why = 1, ''
             except Exception as e:                                   # never lose the e2e figure to the overlap machinery
                 ok, why = 0, ' (FramePipeline failed: %s)' % repr(e)[:200]
+                compute, issue_e2e = compute_eager, 'eager issue'
             if world > 1:                                            # all ranks must take the same path: both hold a collective
                 flag = torch.tensor([ok], device=dev, dtype=torch.int32)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 ok = int(flag.item())
             if ok:
-                step_fn, finalize, mode = step_pipe, (lambda: (pipe.drain(), gather_join())), 'FramePipeline: H2D of frame k+1 / D2H of frame k overlap compute'
+                step_fn, finalize, mode = step_pipe, (lambda: (pipe.drain(), gather_join())), \
+                    'FramePipeline: H2D of frame k+1 / D2H of frame k overlap compute; compute = ' + issue_e2e
             else:
-                mode += why
+                mode = 'serial copies on the compute stream, ' + issue_e2e + why
         e_ms, _, _ = timed(step_fn, K, W, finalize=finalize)
         h2d = sum(f.numel() * 4 for f in feats_h) + 2 * 6 * 16 * 4
         e2e = {'value': world * rays_per_frame / (e_ms / K * 1e-3), 'unit': 'rays/s', 'ms_per_step': e_ms / K,
                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out_h.numel() * 4, 'mode': mode}
+        # what this host's PCIe path gives the same pinned buffers with the GPU otherwise idle (outside every timed region):
+        # when d2h_bytes / d2h_GBps exceeds the device step, the e2e figure above is bound by the link, not by the kernels
+        try:
+            probe_d = torch.empty(out_h.shape, device=dev)
+            feats_d0 = [torch.empty(f.shape, device=dev) for f in feats_h]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            out_h.copy_(probe_d, non_blocking=True)
+            ev[1].record()
+            for dd, hh in zip(feats_d0, feats_h):
+                dd.copy_(hh, non_blocking=True)
+            ev[2].record()
+            torch.cuda.synchronize()
+            e2e['pcie_probe'] = {'d2h_GBps': out_h.numel() * 4 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9,
+                                 'h2d_GBps': sum(f.numel() * 4 for f in feats_h) / (ev[1].elapsed_time(ev[2]) * 1e-3) / 1e9,
+                                 'd2h_ms_per_step_alone': ev[0].elapsed_time(ev[1]), 'h2d_ms_per_step_alone': ev[1].elapsed_time(ev[2])}
+            del probe_d, feats_d0
+        except Exception as e:
+            e2e['pcie_probe'] = {'error': repr(e)[:120]}
 
     if rank != 0:
         if world > 1:

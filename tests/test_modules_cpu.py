@@ -247,3 +247,24 @@ def test_masked_median_and_metric_assembly_cpu():
         r = cal_depth_metric_ref(pred[i], gt[i])
         for k in ('abs_rel', 'sq_rel', 'rmse', 'rmse_log', 'a1', 'a2', 'a3'):
             assert torch.allclose(m[k][i], r[k].float(), rtol=1e-5, atol=1e-7), k
+
+
+def test_ffn_training_path_equals_the_sequential_stack():
+    """FFN.forward's autograd path spells the nn.Sequential out (so that its two Linear layers can go through
+    encoder.train_linear); on CPU train_linear is nn.Linear, so output and gradients must equal `self.layers(x)` exactly,
+    including the dropout draws (same generator state, same order)."""
+    import torch
+    from selfocc_b200.encoder import FFN, train_linear
+    torch.manual_seed(0)
+    ffn = FFN(embed_dims=96, feedforward_channels=192, ffn_drop=0.1).train()
+    x = torch.randn(2, 37, 96, requires_grad=True)
+    torch.manual_seed(5)
+    y = ffn(x)
+    gx, = torch.autograd.grad(y.sum(), x)
+    x2 = x.detach().clone().requires_grad_(True)
+    torch.manual_seed(5)
+    y_ref = x2 + ffn.layers(x2)
+    gx_ref, = torch.autograd.grad(y_ref.sum(), x2)
+    assert torch.equal(y, y_ref) and torch.equal(gx, gx_ref)
+    lin = torch.nn.Linear(96, 96)
+    assert torch.equal(train_linear(lin, x), lin(x))          # CPU tensors: the stock layer
